@@ -1,0 +1,191 @@
+"""Drop-in mirror of the reference's Python layer (python/CudaRenderer.py) on PyTorch.
+
+Same class name, keyword arguments, defaults and getters as python/CudaRenderer.py:34-162; the
+TensorFlow custom-op call (:79-99) becomes a torch.autograd.Function over the C ABI of
+libgvv_b200.so, and the registered gradient (:169-215) becomes its backward.  Tensors are torch
+CUDA tensors in the op's layouts; torch is only used for device memory, streams and autograd
+plumbing -- every kernel is ours.  There is no CPU path: constructing the layer without a CUDA
+device (or without the built library) raises.
+"""
+import hashlib
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _native
+
+_HANDLE_CACHE = OrderedDict()
+_HANDLE_CACHE_MAX = 16
+
+
+def _get_handle(faces, texcoords, N, C, U, V, albedo, shading, ifs, tfs, normal_map, device):
+    """TF caches one OpKernel per attribute set; this is the same cache for gvv handles, so that
+    building the layer every iteration of a fitting loop (as the reference's scripts do,
+    python/test_gradients_VertexColor.py:104-121) does not rebuild topology or scratch."""
+    f = np.ascontiguousarray(np.asarray(faces, dtype=np.int32).reshape(-1))
+    t = np.ascontiguousarray(np.asarray(texcoords, dtype=np.float32).reshape(-1))
+    key = (hashlib.sha1(f.tobytes()).hexdigest(), hashlib.sha1(t.tobytes()).hexdigest(), int(N), int(C), int(U), int(V),
+           albedo, shading, int(ifs), int(tfs), bool(normal_map), str(device))
+    h = _HANDLE_CACHE.get(key)
+    if h is None:
+        h = _native.NativeRenderer(f, t, N, C, U, V, albedo, shading, ifs, tfs, normal_map, device)
+        _HANDLE_CACHE[key] = h
+        while len(_HANDLE_CACHE) > _HANDLE_CACHE_MAX:
+            _HANDLE_CACHE.popitem(last=False)[1].close()
+    else:
+        _HANDLE_CACHE.move_to_end(key)
+    return h
+
+
+def clear_handle_cache():
+    while _HANDLE_CACHE:
+        _HANDLE_CACHE.popitem()[1].close()
+
+
+class _CudaRendererFn(torch.autograd.Function):
+    """cuda_renderer_gpu / cuda_renderer_grad_gpu (CudaRenderer.cpp:5-33, CudaRendererGrad.cpp:6-39)."""
+
+    @staticmethod
+    def forward(ctx, handle, vertex_pos, vertex_color, texture, sh_coeff, target_image, extrinsics, intrinsics):
+        bary, face, render, vnormal, target_out, normal_map = handle.forward(
+            vertex_pos, vertex_color, texture, sh_coeff, target_image, extrinsics, intrinsics)
+        ctx.handle = handle
+        ctx.save_for_backward(vertex_pos, vertex_color, texture, sh_coeff, target_image, extrinsics, intrinsics,
+                              bary, face, vnormal)
+        ctx.mark_non_differentiable(face)
+        ctx.set_materialize_grads(False)
+        # out4 must be a distinct autograd output so a loss on it yields target_buffer_grad
+        return bary, face, render, vnormal, target_out.view_as(target_out), normal_map
+
+    @staticmethod
+    def backward(ctx, g_bary, g_face, g_render, g_vnormal, g_target, g_normal_map):
+        handle = ctx.handle
+        vertex_pos, vertex_color, texture, sh_coeff, target_image, extrinsics, intrinsics, bary, face, vnormal = ctx.saved_tensors
+        # only gradRender and gradTarget are used (CudaRenderer.py:170-171); normal/lighting albedo
+        # and a missing render gradient give zeros (CudaRenderer.py:207-213)
+        if handle.albedo_mode in ("normal", "lighting") or (g_render is None and g_target is None):
+            gpos, gcol, gtex, gsh = (torch.zeros_like(t) for t in (vertex_pos, vertex_color, texture, sh_coeff))
+        else:
+            if g_render is None:
+                g_render = torch.zeros_like(target_image)
+            gpos, gcol, gtex, gsh = handle.backward(g_render, g_target, vertex_pos, vertex_color, texture, sh_coeff,
+                                                    target_image, vnormal, bary, face, extrinsics, intrinsics)
+            gpos, gcol, gtex, gsh = (g.view_as(t) for g, t in ((gpos, vertex_pos), (gcol, vertex_color),
+                                                              (gtex, texture), (gsh, sh_coeff)))
+        need = ctx.needs_input_grad
+        # target image, extrinsics, intrinsics always get zeros (CudaRenderer.py:215)
+        return (None,
+                gpos if need[1] else None, gcol if need[2] else None, gtex if need[3] else None, gsh if need[4] else None,
+                torch.zeros_like(target_image) if need[5] else None,
+                torch.zeros_like(extrinsics) if need[6] else None,
+                torch.zeros_like(intrinsics) if need[7] else None)
+
+
+def _as_cuda(x, device, name):
+    if x is None:
+        raise _native.GvvError(f"{name} is required")
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float32)
+    return torch.as_tensor(np.asarray(x, dtype=np.float32), device=device)
+
+
+class CudaRendererGpu:
+    """Same signature as the reference layer (python/CudaRenderer.py:34-55)."""
+
+    def __init__(self,
+                 faces_attr=[],
+                 texCoords_attr=[],
+                 numberOfVertices_attr=-1,
+                 numberOfCameras_attr=-1,
+                 renderResolutionU_attr=-1,
+                 renderResolutionV_attr=-1,
+                 albedoMode_attr='textured',
+                 shadingMode_attr='shaded',
+                 image_filter_size_attr=1,
+                 texture_filter_size_attr=1,
+                 compute_normal_map_attr=False,
+
+                 vertexPos_input=None,
+                 vertexColor_input=None,
+                 texture_input=None,
+                 shCoeff_input=None,
+                 targetImage_input=None,
+                 extrinsics_input=[],
+                 intrinsics_input=[],
+
+                 nodeName='CudaRenderer',
+                 device=None):
+        self.faces_attr = faces_attr
+        self.texCoords_attr = texCoords_attr
+        self.numberOfVertices_attr = numberOfVertices_attr
+        self.numberOfCameras_attr = numberOfCameras_attr
+        self.renderResolutionU_attr = renderResolutionU_attr
+        self.renderResolutionV_attr = renderResolutionV_attr
+        self.albedoMode_attr = albedoMode_attr
+        self.shadingMode_attr = shadingMode_attr
+        self.image_filter_size_attr = image_filter_size_attr
+        self.texture_filter_size_attr = texture_filter_size_attr
+        self.compute_normal_map_attr = compute_normal_map_attr
+        self.nodeName = nodeName
+
+        if device is None:
+            device = vertexPos_input.device if isinstance(vertexPos_input, torch.Tensor) and vertexPos_input.is_cuda \
+                else torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        self.device = torch.device(device)
+        self.vertexPos_input = _as_cuda(vertexPos_input, self.device, "vertexPos_input")
+        self.vertexColor_input = _as_cuda(vertexColor_input, self.device, "vertexColor_input")
+        self.texture_input = _as_cuda(texture_input, self.device, "texture_input")
+        self.shCoeff_input = _as_cuda(shCoeff_input, self.device, "shCoeff_input")
+        self.targetImage_input = _as_cuda(targetImage_input, self.device, "targetImage_input")
+        self.extrinsics_input = _as_cuda(extrinsics_input, self.device, "extrinsics_input")
+        self.intrinsics_input = _as_cuda(intrinsics_input, self.device, "intrinsics_input")
+
+        self._handle = _get_handle(faces_attr, texCoords_attr, numberOfVertices_attr, numberOfCameras_attr,
+                                   renderResolutionU_attr, renderResolutionV_attr, albedoMode_attr, shadingMode_attr,
+                                   image_filter_size_attr, texture_filter_size_attr, compute_normal_map_attr, self.device)
+        self.cudaRendererOperator = _CudaRendererFn.apply(self._handle, self.vertexPos_input, self.vertexColor_input,
+                                                          self.texture_input, self.shCoeff_input, self.targetImage_input,
+                                                          self.extrinsics_input, self.intrinsics_input)
+
+    # ---- getters (python/CudaRenderer.py:103-162); *TF names kept so call sites do not change ----
+    def getBaryCentricBufferTF(self):
+        return self.cudaRendererOperator[0]
+
+    def getFaceBufferTF(self):
+        return self.cudaRendererOperator[1]
+
+    def getRenderBufferTF(self):
+        return self.cudaRendererOperator[2]
+
+    def getVertexNormalTF(self):
+        return self.cudaRendererOperator[3]
+
+    def getTargetBufferTF(self):
+        return self.cudaRendererOperator[4]
+
+    def getNormalMap(self):
+        if self.compute_normal_map_attr:
+            return self.cudaRendererOperator[5].reshape(self.texture_input.shape)
+        print('Requesting normal map but computation was not enabled!')
+        return None
+
+    def getModelMaskTF(self):
+        face = self.cudaRendererOperator[1]
+        mask = (face >= 0).unsqueeze(-1).expand(*face.shape, 3)
+        return mask.to(torch.float32)
+
+    # OpenCV-style getters: BGR float32 numpy images (cv2 is not needed for a channel flip)
+    def getBaryCentricBufferOpenCV(self, batchId, camId):
+        b = self.cudaRendererOperator[0][batchId][camId].detach().cpu().numpy()
+        return np.concatenate([b, np.zeros_like(b[..., :1])], -1)[..., ::-1].copy()
+
+    def getFaceBufferOpenCV(self, batchId, camId):
+        f = self.cudaRendererOperator[1][batchId][camId].detach().cpu().numpy().astype(np.float32) + 1.0
+        return np.repeat(f[..., None], 3, -1)
+
+    def getRenderBufferOpenCV(self, batchId, camId):
+        return self.cudaRendererOperator[2][batchId][camId].detach().cpu().numpy()[..., ::-1].copy()
+
+    def getNormalMapOpenCV(self, batchId):
+        return self.cudaRendererOperator[5][batchId].detach().cpu().numpy()[..., ::-1].copy()

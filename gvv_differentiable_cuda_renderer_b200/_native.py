@@ -1,0 +1,232 @@
+"""ctypes binding of libgvv_b200.so (include/gvv_b200.h).
+
+This is the only way the Python layer reaches the GPU: there is no CPU fallback and no
+alternative backend.  If the shared library is missing the import of this module fails loudly.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libgvv_b200.so")
+CSRC = os.path.join(_PKG, "csrc")
+SOURCES = ["gvv_api.cu", "gvv_forward.cu", "gvv_backward.cu", "gvv_normalmap.cu", "gvv_microbench.cu"]
+
+ALBEDO_MODES = {"vertexColor": 0, "textured": 1, "normal": 2, "lighting": 3, "foregroundMask": 4}
+SHADING_MODES = {"shaded": 0, "shadeless": 1}
+
+
+def build_library(force=False, verbose=False):
+    """Compile the CUDA sources in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
+    deps.append(os.path.join(_ROOT, "include", "gvv_b200.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH] + srcs
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return LIB_PATH
+
+
+class gvv_desc(ctypes.Structure):
+    _fields_ = [("faces", ctypes.c_void_p), ("num_faces", ctypes.c_int32), ("texcoords", ctypes.c_void_p),
+                ("num_vertices", ctypes.c_int32), ("num_cameras", ctypes.c_int32), ("width", ctypes.c_int32),
+                ("height", ctypes.c_int32), ("albedo_mode", ctypes.c_int32), ("shading_mode", ctypes.c_int32),
+                ("image_filter_size", ctypes.c_int32), ("texture_filter_size", ctypes.c_int32),
+                ("compute_normal_map", ctypes.c_int32), ("device", ctypes.c_int32)]
+
+
+_lib = None
+
+# every symbol include/gvv_b200.h declares
+EXPORTS = ["gvv_create", "gvv_destroy", "gvv_forward", "gvv_backward", "gvv_last_error", "gvv_launch_count",
+           "gvv_debug_copy", "gvv_set_option", "gvv_bench_atomics"]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(the renderer has no CPU or PyTorch fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+        L.gvv_create.argtypes = [ctypes.POINTER(gvv_desc), ctypes.POINTER(vp)]
+        L.gvv_create.restype = ctypes.c_int
+        L.gvv_destroy.argtypes = [vp]
+        L.gvv_destroy.restype = ctypes.c_int
+        L.gvv_forward.argtypes = [vp, i32, i32, i32] + [vp] * 7 + [vp] * 6 + [vp]
+        L.gvv_forward.restype = ctypes.c_int
+        L.gvv_backward.argtypes = [vp, i32, i32, i32] + [vp] * 12 + [vp] * 4 + [vp]
+        L.gvv_backward.restype = ctypes.c_int
+        L.gvv_last_error.restype = ctypes.c_char_p
+        L.gvv_launch_count.argtypes = [vp]
+        L.gvv_launch_count.restype = i64
+        L.gvv_debug_copy.argtypes = [vp, i32, vp, i64, vp]
+        L.gvv_debug_copy.restype = i64
+        L.gvv_set_option.argtypes = [vp, ctypes.c_char_p, i32]
+        L.gvv_set_option.restype = ctypes.c_int
+        L.gvv_bench_atomics.argtypes = [i32, i32, i64, i64, i32, ctypes.POINTER(ctypes.c_double)]
+        L.gvv_bench_atomics.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+class GvvError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise GvvError(f"{what}: [{rc}] {lib().gvv_last_error().decode()}")
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _f32(t, name, device):
+    if t is None:
+        return None
+    if t.device != device:
+        raise GvvError(f"{name} is on {t.device}, the renderer lives on {device}")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class NativeRenderer:
+    """One gvv_handle: immutable topology + scratch on one CUDA device."""
+
+    def __init__(self, faces, texcoords, num_vertices, num_cameras, width, height, albedo_mode, shading_mode,
+                 image_filter_size=1, texture_filter_size=1, compute_normal_map=False, device=None):
+        if albedo_mode not in ALBEDO_MODES:
+            raise GvvError("INVALID ALBEDO MODE")        # CudaRenderer.cpp:60-64
+        if shading_mode not in SHADING_MODES:
+            raise GvvError("INVALID SHADING MODE")       # CudaRenderer.cpp:67-71
+        if not torch.cuda.is_available():
+            raise GvvError("CUDA device required: the renderer has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        f = np.ascontiguousarray(np.asarray(faces, dtype=np.int32).reshape(-1))
+        if f.size % 3:
+            raise GvvError("No triangular faces!")        # CUDABasedRasterization.cpp:38-41
+        self.F = f.size // 3
+        t = None
+        if texcoords is not None and len(texcoords):
+            t = np.ascontiguousarray(np.asarray(texcoords, dtype=np.float32).reshape(-1))
+            if t.size != self.F * 6:
+                raise GvvError("Texture coordinates have wrong dimensionality!")   # CUDABasedRasterization.cpp:49-52
+        self.N, self.C, self.W, self.H = int(num_vertices), int(num_cameras), int(width), int(height)
+        self.albedo_mode, self.shading_mode = albedo_mode, shading_mode
+        self.compute_normal_map = bool(compute_normal_map)
+        d = gvv_desc(f.ctypes.data, self.F, t.ctypes.data if t is not None else None, self.N, self.C, self.W, self.H,
+                     ALBEDO_MODES[albedo_mode], SHADING_MODES[shading_mode], int(image_filter_size),
+                     int(texture_filter_size), int(self.compute_normal_map), self.device.index or 0)
+        h = ctypes.c_void_p()
+        _check(lib().gvv_create(ctypes.byref(d), ctypes.byref(h)), "gvv_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().gvv_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key, value):
+        _check(lib().gvv_set_option(self._h, key.encode(), int(value)), "gvv_set_option")
+
+    @property
+    def launch_count(self):
+        return int(lib().gvv_launch_count(self._h))
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def forward(self, vertex_pos, vertex_color, texture, sh_coeff, target_image, extrinsics, intrinsics):
+        dev = self.device
+        vertex_pos = _f32(vertex_pos, "vertex_pos", dev)
+        vertex_color = _f32(vertex_color, "vertex_color", dev)
+        texture = _f32(texture, "texture", dev)
+        sh_coeff = _f32(sh_coeff, "sh_coeff", dev)
+        target_image = _f32(target_image, "target_image", dev)
+        extrinsics = _f32(extrinsics, "extrinsics", dev)
+        intrinsics = _f32(intrinsics, "intrinsics", dev)
+        # B, texH, texW come from the texture tensor, as in CudaRenderer.cpp:207-209
+        B, texH, texW = int(texture.shape[0]), int(texture.shape[1]), int(texture.shape[2])
+        C, N, W, H = self.C, self.N, self.W, self.H
+        if vertex_pos.numel() != B * N * 3 or sh_coeff.numel() != B * C * 27 or \
+           extrinsics.numel() != B * C * 12 or intrinsics.numel() != B * C * 9:
+            raise GvvError("input tensor sizes do not match batch/cameras/vertices")
+        o = dict(device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            bary = torch.empty((B, C, H, W, 2), **o)
+            face = torch.empty((B, C, H, W), device=dev, dtype=torch.int32)
+            render = torch.empty((B, C, H, W, 3), **o)
+            vnormal = torch.empty((B, C, N, 3), **o)
+            normal_map = torch.zeros((B, texH, texW, 3), **o) if self.compute_normal_map else torch.empty((0,), **o)
+            if self.compute_normal_map:
+                # rasterisation is skipped (CUDABasedRasterization.cu:463-466): the raster outputs stay
+                # unwritten in the reference; we define them as background
+                bary.zero_(); face.fill_(-1); render.zero_(); render[..., 1] = 1.0
+            # out4 is a copy of in4 in the reference; aliasing it saves 12 B/px and keeps the gradient path
+            target_out = target_image
+            _check(lib().gvv_forward(self._h, B, texH, texW, _ptr(vertex_pos), _ptr(vertex_color), _ptr(texture),
+                                     _ptr(sh_coeff), _ptr(target_image), _ptr(extrinsics), _ptr(intrinsics),
+                                     _ptr(bary), _ptr(face), _ptr(render), _ptr(vnormal), _ptr(target_out),
+                                     _ptr(normal_map) if self.compute_normal_map else None, self._stream()),
+                   "gvv_forward")
+        return bary, face, render, vnormal, target_out, normal_map
+
+    def backward(self, render_grad, target_grad, vertex_pos, vertex_color, texture, sh_coeff, target_image,
+                 vertex_normal, bary, face, extrinsics, intrinsics):
+        dev = self.device
+        B, texH, texW = int(texture.shape[0]), int(texture.shape[1]), int(texture.shape[2])
+        C, N = self.C, self.N
+        args = [_f32(t, n, dev) for t, n in [(render_grad, "render_buffer_grad"), (vertex_pos, "vertex_pos"),
+                                              (vertex_color, "vertex_color"), (texture, "texture"),
+                                              (sh_coeff, "sh_coeff"), (target_image, "target_image"),
+                                              (vertex_normal, "vertex_normal"), (bary, "barycentric_buffer")]]
+        face = face.contiguous()
+        target_grad = _f32(target_grad, "target_buffer_grad", dev)
+        extrinsics = _f32(extrinsics, "extrinsics", dev)
+        intrinsics = _f32(intrinsics, "intrinsics", dev)
+        o = dict(device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            gpos = torch.empty((B, N, 3), **o)
+            gcol = torch.empty((B, N, 3), **o)
+            gtex = torch.empty((B, texH, texW, 3), **o)
+            gsh = torch.empty((B, C, 27), **o)
+            _check(lib().gvv_backward(self._h, B, texH, texW, *[_ptr(a) for a in args], _ptr(face), _ptr(target_grad),
+                                      _ptr(extrinsics), _ptr(intrinsics), _ptr(gpos), _ptr(gcol), _ptr(gtex),
+                                      _ptr(gsh), self._stream()), "gvv_backward")
+        return gpos, gcol, gtex, gsh
+
+    def debug_copy(self, which, nbytes):
+        buf = np.empty(nbytes, dtype=np.uint8)
+        n = lib().gvv_debug_copy(self._h, which, buf.ctypes.data, nbytes, self._stream())
+        if n < 0:
+            raise GvvError("gvv_debug_copy failed")
+        return buf[:min(n, nbytes)]
+
+
+def bench_atomics(kind, n_addr, n_ops, iters=10, device=0):
+    out = ctypes.c_double(0.0)
+    _check(lib().gvv_bench_atomics(device, kind, n_addr, n_ops, iters, ctypes.byref(out)), "gvv_bench_atomics")
+    return out.value

@@ -1,0 +1,298 @@
+// gvv_api.cu -- C-ABI shim (include/gvv_b200.h): handle life cycle, argument validation, scratch.
+//
+// Mirrors the reference's op boundary (CudaRenderer.cpp / CudaRendererGrad.cpp) minus TensorFlow:
+// the per-batch host loop of Compute() (CudaRenderer.cpp:309-328) is gone -- one call enqueues
+// the kernels for all B*C views on the caller's stream and returns without synchronising.
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <vector>
+#include <new>
+#include "gvv_internal.h"
+
+using namespace gvv;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(GVV_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" const char* gvv_last_error(void) { return g_err; }
+
+template <typename T>
+static cudaError_t dmalloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  return cudaMalloc((void**)p, count * sizeof(T));
+}
+
+static void free_scratch(Scratch& s) {
+  cudaFree(s.cams); cudaFree(s.proj); cudaFree(s.vscaled); cudaFree(s.vnorm4); cudaFree(s.vcol4);
+  cudaFree(s.tileCount); cudaFree(s.tileCursor); cudaFree(s.tileOffset); cudaFree(s.bigCount);
+  cudaFree(s.bigList); cudaFree(s.bins); cudaFree(s.gnorm);
+  s = Scratch();
+}
+
+static void set_tile(gvv_renderer* h, int tile) {
+  h->tile = tile;
+  h->tilesX = (h->W + tile - 1) / tile;
+  h->tilesY = (h->H + tile - 1) / tile;
+  h->nT = h->tilesX * h->tilesY;
+}
+
+// Scratch is sized for the largest batch seen; growing it is the only time a call allocates.
+static int ensure_scratch(gvv_renderer* h, int B, cudaStream_t st) {
+  Scratch& s = h->s;
+  const int V = B * h->C;
+  if (V <= s.capViews && B <= s.capBatch) return GVV_OK;
+  CK(cudaStreamSynchronize(st));
+  free_scratch(s);
+  const size_t N = h->N, F = h->F, nT = h->nT;
+  cudaError_t e = cudaSuccess;
+  auto acc = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  acc(dmalloc(&s.cams, (size_t)V));
+  acc(dmalloc(&s.proj, (size_t)V * N));
+  acc(dmalloc(&s.vscaled, (size_t)B * N));
+  acc(dmalloc(&s.vnorm4, (size_t)B * N));
+  acc(dmalloc(&s.vcol4, (size_t)B * N));
+  acc(dmalloc(&s.tileCount, (size_t)V * nT));
+  acc(dmalloc(&s.tileCursor, (size_t)V * nT));
+  acc(dmalloc(&s.tileOffset, (size_t)V * nT));
+  acc(dmalloc(&s.bigCount, (size_t)V));
+  acc(dmalloc(&s.bigList, (size_t)V * F));
+  acc(dmalloc(&s.bins, (size_t)V * F * kMaxSmallTiles));
+  acc(dmalloc(&s.gnorm, (size_t)B * N * 3));
+  if (e != cudaSuccess) {
+    free_scratch(s);
+    return fail(GVV_ENOMEM, "scratch allocation for %d views failed: %s", V, cudaGetErrorString(e));
+  }
+  CK(cudaMemsetAsync(s.tileCount, 0, (size_t)V * nT * sizeof(int), st));
+  CK(cudaMemsetAsync(s.tileCursor, 0, (size_t)V * nT * sizeof(int), st));
+  CK(cudaMemsetAsync(s.bigCount, 0, (size_t)V * sizeof(int), st));
+  s.capViews = V;
+  s.capBatch = B;
+  return GVV_OK;
+}
+
+extern "C" int gvv_create(const gvv_desc* d, gvv_handle* out) {
+  if (!d || !out) return fail(GVV_EINVAL, "gvv_create: null argument");
+  *out = nullptr;
+  // attribute checks of CudaRenderer.cpp:47-76 (errors instead of prints / OP_REQUIRES)
+  if (d->num_vertices <= 0) return fail(GVV_EINVAL, "number_of_vertices not set!");
+  if (d->num_cameras <= 0) return fail(GVV_EINVAL, "number_of_cameras not set!");
+  if (d->width <= 0) return fail(GVV_EINVAL, "render_resolution_u not set!");
+  if (d->height <= 0) return fail(GVV_EINVAL, "render_resolution_v not set!");
+  if (d->width > 65535 || d->height > 65535) return fail(GVV_EINVAL, "render resolution above 65535 is not supported");
+  if (d->albedo_mode < 0 || d->albedo_mode > 4) return fail(GVV_EINVAL, "INVALID ALBEDO MODE");
+  if (d->shading_mode < 0 || d->shading_mode > 1) return fail(GVV_EINVAL, "INVALID SHADING MODE");
+  if (d->num_faces < 0 || (d->num_faces > 0 && !d->faces)) return fail(GVV_EINVAL, "faces missing");
+  if (d->albedo_mode == GVV_ALBEDO_TEXTURED && d->num_faces > 0 && !d->texcoords)
+    return fail(GVV_EINVAL, "textured albedo needs texture_coordinates");
+  for (int i = 0; i < d->num_faces * 3; ++i)
+    if (d->faces[i] < 0 || d->faces[i] >= d->num_vertices)
+      return fail(GVV_EINVAL, "face %d references vertex %d outside [0,%d)", i / 3, d->faces[i], d->num_vertices);
+  CK(cudaSetDevice(d->device));
+
+  gvv_renderer* h = new (std::nothrow) gvv_renderer();
+  if (!h) return fail(GVV_ENOMEM, "out of host memory");
+  h->device = d->device;
+  h->F = d->num_faces; h->N = d->num_vertices; h->C = d->num_cameras; h->W = d->width; h->H = d->height;
+  h->albedo = d->albedo_mode;
+  h->shading = d->shading_mode;
+  if (h->albedo == GVV_ALBEDO_FOREGROUND_MASK) h->shading = GVV_SHADING_SHADELESS;   // CudaRenderer.cpp:72-76
+  h->imgFilter = d->image_filter_size;
+  h->texFilter = d->texture_filter_size;
+  h->computeNormalMap = d->compute_normal_map ? 1 : 0;
+  set_tile(h, 32);
+
+  // topology: faces padded to int4; vertex -> incident faces CSR by counting sort, O(N+F)
+  // (reference: O(N*F) double loop, CUDABasedRasterization.cpp:125-154; same ascending face order;
+  //  a face that repeats a vertex is listed once for it, as there).
+  const int F = h->F, N = h->N;
+  std::vector<int4> f4((size_t)F);
+  std::vector<int> offs((size_t)N + 1, 0);
+  auto distinct = [&](int f, int k) {
+    const int* v = d->faces + 3 * f;
+    for (int j = 0; j < k; ++j) if (v[j] == v[k]) return false;
+    return true;
+  };
+  for (int f = 0; f < F; ++f) {
+    f4[f] = make_int4(d->faces[3 * f], d->faces[3 * f + 1], d->faces[3 * f + 2], 0);
+    for (int k = 0; k < 3; ++k) if (distinct(f, k)) offs[d->faces[3 * f + k] + 1]++;
+  }
+  for (int n = 0; n < N; ++n) offs[n + 1] += offs[n];
+  std::vector<int> list((size_t)offs[N]);
+  std::vector<int> cur(offs.begin(), offs.end() - 1);
+  for (int f = 0; f < F; ++f)
+    for (int k = 0; k < 3; ++k) if (distinct(f, k)) list[cur[d->faces[3 * f + k]]++] = f;
+
+  cudaError_t e = cudaSuccess;
+  auto acc = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  acc(dmalloc(&h->faces4, (size_t)F));
+  acc(dmalloc(&h->vfOffsets, (size_t)N + 1));
+  acc(dmalloc(&h->vfList, list.size()));
+  if (e == cudaSuccess && F) acc(cudaMemcpy(h->faces4, f4.data(), sizeof(int4) * F, cudaMemcpyHostToDevice));
+  if (e == cudaSuccess) acc(cudaMemcpy(h->vfOffsets, offs.data(), sizeof(int) * (N + 1), cudaMemcpyHostToDevice));
+  if (e == cudaSuccess && !list.empty()) acc(cudaMemcpy(h->vfList, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice));
+  if (d->texcoords && F) {
+    h->hasTexcoords = true;
+    acc(dmalloc(&h->texcoords, (size_t)F * 6));
+    if (e == cudaSuccess) acc(cudaMemcpy(h->texcoords, d->texcoords, sizeof(float) * 6 * F, cudaMemcpyHostToDevice));
+  }
+  if (e != cudaSuccess) {
+    gvv_destroy(h);
+    return fail(GVV_ECUDA, "topology upload failed: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return GVV_OK;
+}
+
+extern "C" int gvv_destroy(gvv_handle h) {
+  if (!h) return GVV_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  free_scratch(h->s);
+  cudaFree(h->faces4); cudaFree(h->texcoords); cudaFree(h->vfOffsets); cudaFree(h->vfList); cudaFree(h->texelTable);
+  delete h;
+  return GVV_OK;
+}
+
+extern "C" int gvv_set_option(gvv_handle h, const char* key, int32_t value) {
+  if (!h || !key) return fail(GVV_EINVAL, "gvv_set_option: null argument");
+  if (!strcmp(key, "tile")) {
+    if (value != 16 && value != 32) return fail(GVV_EINVAL, "tile must be 16 or 32");
+    if (value != h->tile) {
+      cudaSetDevice(h->device);
+      cudaDeviceSynchronize();
+      free_scratch(h->s);
+      set_tile(h, value);
+    }
+    return GVV_OK;
+  }
+  return fail(GVV_EINVAL, "unknown option '%s'", key);
+}
+
+extern "C" int64_t gvv_launch_count(gvv_handle h) { return h ? h->launches : 0; }
+
+extern "C" int gvv_forward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
+                           const float* vertex_pos, const float* vertex_color, const float* texture,
+                           const float* sh_coeff, const float* target_image,
+                           const float* extrinsics, const float* intrinsics,
+                           float* bary, int32_t* face, float* render, float* vertex_normal,
+                           float* target_image_out, float* normal_map, void* stream) {
+  if (!h) return fail(GVV_EINVAL, "gvv_forward: null handle");
+  if (B <= 0) return fail(GVV_EINVAL, "gvv_forward: batch must be positive");
+  if (!vertex_pos || !sh_coeff || !extrinsics || !intrinsics || !vertex_normal)
+    return fail(GVV_EINVAL, "gvv_forward: null input/output pointer");
+  if (!h->computeNormalMap && (!bary || !face || !render)) return fail(GVV_EINVAL, "gvv_forward: null output pointer");
+  if (h->albedo == GVV_ALBEDO_VERTEX_COLOR && !vertex_color) return fail(GVV_EINVAL, "gvv_forward: vertex_color is null");
+  if (h->albedo == GVV_ALBEDO_TEXTURED && (!texture || texH <= 0 || texW <= 0)) return fail(GVV_EINVAL, "gvv_forward: texture missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  const int rc = ensure_scratch(h, B, st);
+  if (rc) return rc;
+
+  FwdArgs a;
+  a.B = B; a.C = h->C; a.N = h->N; a.F = h->F; a.W = h->W; a.H = h->H; a.texH = texH; a.texW = texW;
+  a.albedo = h->albedo; a.shading = h->shading;
+  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT;
+  a.vertex_pos = vertex_pos; a.vertex_color = vertex_color; a.texture = texture; a.sh_coeff = sh_coeff;
+  a.extrinsics = extrinsics; a.intrinsics = intrinsics; a.texcoords = h->texcoords;
+  a.faces4 = h->faces4; a.vfOffsets = h->vfOffsets; a.vfList = h->vfList;
+  a.bary = bary; a.face = face; a.render = render; a.vertex_normal = vertex_normal;
+  a.s = h->s;
+
+  // out4 is a copy of in4 (CudaRenderer.cpp:286); non-blocking here
+  if (target_image && target_image_out && target_image != target_image_out)
+    CK(cudaMemcpyAsync(target_image_out, target_image, sizeof(float) * 3 * (size_t)B * h->C * h->W * h->H,
+                       cudaMemcpyDeviceToDevice, st));
+
+  int n;
+  if (h->computeNormalMap) {
+    // compute_normal_map replaces rasterisation (CUDABasedRasterization.cu:463-466)
+    if (!normal_map || texH <= 0 || texW <= 0) return fail(GVV_EINVAL, "gvv_forward: normal_map output / texture size missing");
+    if (!h->hasTexcoords) return fail(GVV_EINVAL, "gvv_forward: compute_normal_map needs texture_coordinates");
+    if (!h->texelTable || h->tableH != texH || h->tableW != texW) {
+      CK(cudaStreamSynchronize(st));
+      cudaFree(h->texelTable); h->texelTable = nullptr;
+      CK(dmalloc(&h->texelTable, (size_t)texH * texW));
+      const int k = launch_build_texel_table(h->texcoords, h->F, texH, texW, h->texelTable, st);
+      if (k < 0) return fail(GVV_ECUDA, "texel table build failed: %s", cudaGetErrorString(cudaGetLastError()));
+      h->launches += k;
+      h->tableH = texH; h->tableW = texW;
+    }
+    n = launch_normal_map(a, h->texelTable, normal_map, st);
+  } else {
+    n = launch_forward(a, st);
+  }
+  if (n < 0) return fail(GVV_ECUDA, "forward launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  h->launches += n;
+  return GVV_OK;
+}
+
+extern "C" int gvv_backward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
+                            const float* render_grad,
+                            const float* vertex_pos, const float* vertex_color, const float* texture,
+                            const float* sh_coeff, const float* target_image, const float* vertex_normal,
+                            const float* bary, const int32_t* face, const float* target_grad,
+                            const float* extrinsics, const float* intrinsics,
+                            float* vpos_grad, float* vcol_grad, float* tex_grad, float* sh_grad, void* stream) {
+  if (!h) return fail(GVV_EINVAL, "gvv_backward: null handle");
+  if (B <= 0) return fail(GVV_EINVAL, "gvv_backward: batch must be positive");
+  // the Python gradient only calls the op for these modes (CudaRenderer.py:175); the kernel
+  // itself prints "Unsupported color mode" otherwise (CUDABasedRasterizationGrad.cu:391-394)
+  if (h->albedo == GVV_ALBEDO_NORMAL || h->albedo == GVV_ALBEDO_LIGHTING)
+    return fail(GVV_EUNSUPPORTED, "Unsupported color mode in renderer gradient!");
+  if (!render_grad || !vertex_pos || !sh_coeff || !vertex_normal || !bary || !face || !extrinsics || !intrinsics ||
+      !vpos_grad || !vcol_grad || !sh_grad)
+    return fail(GVV_EINVAL, "gvv_backward: null input/output pointer");
+  if (h->albedo != GVV_ALBEDO_FOREGROUND_MASK && !vertex_color) return fail(GVV_EINVAL, "gvv_backward: vertex_color is null");
+  if (h->albedo == GVV_ALBEDO_TEXTURED && (!texture || !tex_grad || texH <= 0 || texW <= 0))
+    return fail(GVV_EINVAL, "gvv_backward: texture / texture_grad missing");
+  if (target_grad && !target_image) return fail(GVV_EINVAL, "gvv_backward: target_buffer_grad given without target_image");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  const int rc = ensure_scratch(h, B, st);
+  if (rc) return rc;
+
+  BwdArgs a;
+  a.B = B; a.C = h->C; a.N = h->N; a.F = h->F; a.W = h->W; a.H = h->H; a.texH = texH; a.texW = texW;
+  a.albedo = h->albedo; a.shading = h->shading; a.imgFilter = h->imgFilter;
+  a.render_grad = render_grad; a.target_grad = target_grad; a.vertex_pos = vertex_pos; a.vertex_color = vertex_color;
+  a.texture = texture; a.sh_coeff = sh_coeff; a.target_image = target_image; a.vertex_normal = vertex_normal;
+  a.bary = bary; a.extrinsics = extrinsics; a.intrinsics = intrinsics; a.texcoords = h->texcoords;
+  a.face = face; a.faces4 = h->faces4; a.vfOffsets = h->vfOffsets; a.vfList = h->vfList;
+  a.vpos_grad = vpos_grad; a.vcol_grad = vcol_grad; a.tex_grad = tex_grad; a.sh_grad = sh_grad;
+  a.s = h->s;
+  const int n = launch_backward(a, st);
+  if (n < 0) return fail(GVV_ECUDA, "backward launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  h->launches += n;
+  return GVV_OK;
+}
+
+extern "C" int64_t gvv_debug_copy(gvv_handle h, int32_t which, void* dst, int64_t capacity, void* stream) {
+  if (!h || !dst) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaSetDevice(h->device);
+  const void* src = nullptr;
+  int64_t bytes = 0;
+  if (which == 0) { src = h->s.cams; bytes = (int64_t)h->s.capViews * sizeof(CamRec); }
+  else if (which == 1) { src = h->s.proj; bytes = (int64_t)h->s.capViews * h->N * sizeof(float4); }
+  else return -1;
+  if (!src) return 0;
+  const int64_t n = bytes < capacity ? bytes : capacity;
+  if (cudaMemcpyAsync(dst, src, (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+  return bytes;
+}

@@ -1,0 +1,387 @@
+// gvv_backward.cu -- backward pass of the rasteriser for sm_100a.
+//
+// Reference: renderBuffersGradGPU (CUDABasedRasterizationGrad.cu:624-635): one thread per pixel,
+// 157 registers, ~214 scalar float atomics per covered pixel, 27 of them on the same 27 SH
+// addresses for every pixel of a camera.  Here, for all B*C views in one go:
+//
+//   camera_kernel        (shared with the forward)                                   (ref :17-61)
+//   zero_kernel          all four gradient outputs + the vertex-normal gradient      (ref :68-107)
+//   pixel_grad_kernel    one warp per 32-pixel scanline segment.  The 27 per-vertex values of a
+//                        pixel (9 colour, 9 position, 9 vertex-normal gradient) are transposed
+//                        through shared memory so that lane j sums value j over each run of
+//                        pixels that see the same triangle: ONE warp-wide atomic per run instead
+//                        of 27 per pixel.  SH gradients are reduced warp -> block -> 27 atomics.
+//   normal_term_kernel   mesh-space pass for the vertex-normal -> position term (ref :559-615):
+//                        the reference loops over every face incident to the pixel's three
+//                        vertices (27*deg atomics per pixel); that sum is linear in the per-pixel
+//                        factor q, so we scatter Gn[v_i] += bcc_i*q per pixel and apply the
+//                        cross-product Jacobians (RendererUtil.h:422-539) once per vertex here,
+//                        as a gather over the CSR -- no atomics, same mathematics.
+#include "gvv_internal.h"
+
+namespace gvv {
+
+#define FULL_MASK 0xffffffffu
+
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ V3 ldv3(const float* __restrict__ p, size_t i) { return v3(__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2)); }
+
+// ------------------------------------------------------------------------------------------------
+struct ZeroArgs { float* p[5]; long long n[5]; };
+
+__global__ void zero_kernel(ZeroArgs z) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    float* p = z.p[r];
+    if (!p) continue;
+    const long long n = z.n[r];
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      float4* p4 = reinterpret_cast<float4*>(p);
+      const long long n4 = n >> 2;
+      for (long long i = t0; i < n4; i += stride) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (long long i = (n4 << 2) + t0; i < n; i += stride) p[i] = 0.f;
+    } else {
+      for (long long i = t0; i < n; i += stride) p[i] = 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// d(alpha*a + beta*b)/d(v0,v1,v2) for the barycentrics of the ray/plane hit: the product
+// [alpha beta gamma] * dJBCDVerpos (RendererUtil.h:670-861) with the third row = -(row0+row1)
+// folded into alpha,beta.  The reference builds the 3x9 Jacobian column by column; this is the
+// same derivative in reverse mode.  Early-out conditions as RendererUtil.h:682-685.
+__device__ __forceinline__ void bary_vjp(V3 o, V3 d, V3 v0, V3 v1, V3 v2, float alpha, float beta, V3& g0, V3& g1, V3& g2) {
+  g0 = g1 = g2 = v3(0.f, 0.f, 0.f);
+  const V3 e01 = v1 - v0, e02 = v2 - v0;
+  const V3 N = cross(e01, e02);
+  const float D = dot(N, N);
+  const float nd = dot(d, N);
+  const float il = rsqrtf(dot(d, d)), in = rsqrtf(D);
+  if (fabsf(dot(il * d, in * N)) < 0.001f || fabsf(D * D) < 0.001f) return;
+  const V3 w = v0 - o;
+  const float t = dot(w, N) / nd;
+  const V3 P = o + t * d;
+  const V3 E1 = v2 - v1, p1 = P - v1, C1 = cross(E1, p1);
+  const V3 E2 = v0 - v2, p2 = P - v2, C2 = cross(E2, p2);
+  const float A = dot(N, C1), Bn = dot(N, C2);
+  const float Ab = alpha / D, Bb = beta / D;
+  const float Db = -(alpha * A + beta * Bn) / (D * D);
+  V3 Nb = Ab * C1 + Bb * C2 + (2.f * Db) * N;
+  const V3 C1b = Ab * N, C2b = Bb * N;
+  const V3 E1b = cross(p1, C1b), p1b = cross(C1b, E1);
+  const V3 E2b = cross(p2, C2b), p2b = cross(C2b, E2);
+  const V3 Pb = p1b + p2b;
+  const float tb = dot(Pb, d);
+  const float mb = tb / nd;
+  const float ndb = -tb * t / nd;
+  Nb = Nb + mb * w + ndb * d;
+  const V3 e01b = cross(e02, Nb), e02b = cross(Nb, e01);
+  g0 = E2b + mb * N - e01b - e02b;
+  g1 = e01b - p1b - E1b;
+  g2 = e02b - p2b + E1b - E2b;
+}
+
+struct PixelParams {
+  const float *render_grad, *target_grad, *vertex_pos, *vertex_color, *texture, *sh_coeff, *target_image,
+      *vertex_normal, *bary, *texcoords;
+  const int32_t* face;
+  const int4* faces4;
+  const CamRec* cams;
+  float *vpos_grad, *vcol_grad, *tex_grad, *sh_grad, *gnorm;
+  int C, N, W, H, texH, texW, albedo, shading, imgFilter;
+};
+
+constexpr int kVals = 27;
+
+__global__ void __launch_bounds__(256)
+pixel_grad_kernel(const PixelParams p) {
+  __shared__ float buf[8][32 * kVals];
+  __shared__ float shPart[8][kVals];
+  __shared__ CamRec cam;
+  __shared__ float shc[27];
+
+  const int view = blockIdx.z, b = view / p.C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + warp;
+  const bool inb = x < p.W && y < p.H;
+  const size_t pix = (size_t)view * p.W * p.H + (size_t)y * p.W + x;
+  const int face = inb ? __ldg(p.face + pix) : -1;
+  const bool covered = face >= 0;
+  const bool shaded = p.shading == GVV_SHADING_SHADED;
+
+  if (__syncthreads_or(covered) == 0) return;   // nothing visible in this 32x8 block
+  if (tid < 64) reinterpret_cast<float*>(&cam)[tid] = reinterpret_cast<const float*>(p.cams + view)[tid];
+  if (tid >= 64 && tid < 64 + 27) shc[tid - 64] = p.sh_coeff[(size_t)view * 27 + (tid - 64)];
+  __syncthreads();
+
+  float* mybuf = buf[warp];
+  const unsigned cv = __ballot_sync(FULL_MASK, covered);
+  float shv[kVals];
+#pragma unroll
+  for (int j = 0; j < kVals; ++j) shv[j] = 0.f;
+
+  if (cv) {
+    float val[kVals];
+#pragma unroll
+    for (int j = 0; j < kVals; ++j) val[j] = 0.f;
+    if (covered) {
+      // ---- per-pixel setup (CUDABasedRasterizationGrad.cu:205-240) ----
+      const F3 rdx = ray_dir_exact(cam.Pinv, cam.ro, (float)x + 0.5f, (float)y + 0.5f);
+      const V3 d = v3(rdx.x, rdx.y, rdx.z), o = v3(cam.ro[0], cam.ro[1], cam.ro[2]);
+      const float2 ab = __ldg(reinterpret_cast<const float2*>(p.bary) + pix);
+      const float bc[3] = {ab.x, ab.y, 1.f - ab.x - ab.y};
+      const int4 fc = __ldg(p.faces4 + face);
+      const float* pos = p.vertex_pos + (size_t)b * p.N * 3;
+      const float* nor = p.vertex_normal + (size_t)view * p.N * 3;
+      const V3 p0 = ldv3(pos, fc.x), p1 = ldv3(pos, fc.y), p2 = ldv3(pos, fc.z);
+      const V3 n0 = ldv3(nor, fc.x), n1 = ldv3(nor, fc.y), n2 = ldv3(nor, fc.z);
+      const V3 nUn = bc[0] * n0 + bc[1] * n1 + bc[2] * n2;
+      const float len = sqrtf(dot(nUn, nUn));
+      V3 n = v3(nUn.x / len, nUn.y / len, nUn.z / len);
+      const bool flipped = dot(n, d) > 0.f;
+      if (flipped) n = v3(-n.x, -n.y, -n.z);
+
+      // SH basis (getIllum / getJLiGm, RendererUtil.h:179-214,351-364)
+      const float Y[9] = {1.f, n.y, n.z, n.x, n.x * n.y, n.z * n.y, 3.f * n.z * n.z - 1.f, n.x * n.z, n.x * n.x - n.y * n.y};
+      float light[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s += shc[ch * 9 + k] * Y[k];
+        light[ch] = s;
+      }
+      const float3 g = make_float3(__ldg(p.render_grad + 3 * pix), __ldg(p.render_grad + 3 * pix + 1), __ldg(p.render_grad + 3 * pix + 2));
+      const float gl[3] = {shaded ? g.x * light[0] : g.x, shaded ? g.y * light[1] : g.y, shaded ? g.z * light[2] : g.z};
+
+      // ---- albedo (:242-319) and its gradients (:327-395) ----
+      float alb[3] = {0.f, 0.f, 0.f};
+      if (p.albedo == GVV_ALBEDO_VERTEX_COLOR) {
+        const float* col = p.vertex_color + (size_t)b * p.N * 3;
+        const V3 c0 = ldv3(col, fc.x), c1 = ldv3(col, fc.y), c2 = ldv3(col, fc.z);
+        const V3 al = bc[0] * c0 + bc[1] * c1 + bc[2] * c2;
+        alb[0] = al.x; alb[1] = al.y; alb[2] = al.z;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) val[i * 3 + ch] = gl[ch] * bc[i];
+      } else if (p.albedo == GVV_ALBEDO_TEXTURED) {
+        const float* tc = p.texcoords + (size_t)face * 6;
+        float u = (__ldg(tc + 0) * bc[0] + __ldg(tc + 2) * bc[1] + __ldg(tc + 4) * bc[2]) * p.texW;
+        float v = ((1.f - __ldg(tc + 1)) * bc[0] + (1.f - __ldg(tc + 3)) * bc[1] + (1.f - __ldg(tc + 5)) * bc[2]) * p.texH;
+        u = fminf(fmaxf(u, 0.f), (float)(p.texW - 1));
+        v = fminf(fmaxf(v, 0.f), (float)(p.texH - 1));
+        const float LU = (float)(int)(u - 0.5f) + 0.5f, HU = (float)(int)(u - 0.5f) + 1.5f;
+        const float LV = (float)(int)(v - 0.5f) + 0.5f, HV = (float)(int)(v - 0.5f) + 1.5f;
+        const float* tex = p.texture + (size_t)b * p.texH * p.texW * 3;
+        const int lu = (int)LU, hu = (int)HU, lv = (int)LV, hv = (int)HV;
+        // bilinear mix exactly as written in :311-312 (the forward uses the nearest texel)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float cLULV = __ldg(tex + 3 * ((size_t)p.texW * lv + lu) + ch), cLUHV = __ldg(tex + 3 * ((size_t)p.texW * hv + lu) + ch);
+          const float cHULV = __ldg(tex + 3 * ((size_t)p.texW * lv + hu) + ch), cHUHV = __ldg(tex + 3 * ((size_t)p.texW * hv + hu) + ch);
+          alb[ch] = (v - LV) * ((u - LU) * cLULV + (HU - u) * cHULV) + (HV - v) * ((u - LU) * cLUHV + (HU - u) * cHUHV);
+        }
+        if (!flipped) {   // unweighted add to texel (LV,LU) (:382-384)
+          float* tg = p.tex_grad + ((size_t)b * p.texH * p.texW + (size_t)p.texW * lv + lu) * 3;
+          atomicAdd(tg + 0, gl[0]); atomicAdd(tg + 1, gl[1]); atomicAdd(tg + 2, gl[2]);
+        }
+      }
+      const float gA[3] = {g.x * alb[0], g.y * alb[1], g.z * alb[2]};
+
+      if (shaded) {
+        // ---- SH gradient (:402-436) ----
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+          for (int k = 0; k < 9; ++k) shv[ch * 9 + k] = gA[ch] * Y[k];
+        // ---- position gradient through the shading normal (:458-525) ----
+        V3 u3 = v3(0.f, 0.f, 0.f);   // (g*albedo) * JLiNo  (RendererUtil.h:371-391)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float* s = shc + ch * 9;
+          u3.x += gA[ch] * (s[3] + s[4] * n.y + s[7] * n.z + s[8] * 2.f * n.x);
+          u3.y += gA[ch] * (s[1] + s[4] * n.x + s[5] * n.z + s[8] * -2.f * n.y);
+          u3.z += gA[ch] * (s[2] + s[5] * n.y + s[6] * 6.f * n.z + s[7] * n.x);
+        }
+        // * JNoNu (:398-415): (len^2 I - nUn nUn^T) / len^3, evaluated on the UNflipped normal
+        const float l2 = len * len, l3 = l2 * len, un = dot(u3, nUn);
+        const V3 q = v3((l2 * u3.x - un * nUn.x) / l3, (l2 * u3.y - un * nUn.y) / l3, (l2 * u3.z - un * nUn.z) / l3);
+        // * JNoBc * JBcVp: direct dependence of the barycentrics on the triangle's own vertices
+        const float r0 = dot(q, n0), r1 = dot(q, n1), r2 = dot(q, n2);
+        V3 g0, g1, g2;
+        bary_vjp(o, d, p0, p1, p2, r0 - r2, r1 - r2, g0, g1, g2);
+        val[9] = g0.x; val[10] = g0.y; val[11] = g0.z;
+        val[12] = g1.x; val[13] = g1.y; val[14] = g1.z;
+        val[15] = g2.x; val[16] = g2.y; val[17] = g2.z;
+        // vertex-normal gradient, finished in normal_term_kernel
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { val[18 + i * 3] = bc[i] * q.x; val[19 + i * 3] = bc[i] * q.y; val[20 + i * 3] = bc[i] * q.z; }
+      }
+
+      // ---- model-to-data term (:531-555) ----
+      if (p.target_grad) {
+        const int fs = p.imgFilter;
+        V3 dIu = v3(0.f, 0.f, 0.f), dIv = v3(0.f, 0.f, 0.f);
+        if (x >= fs + 1 && y >= fs + 1 && x < p.W - (fs + 1) && y < p.H - (fs + 1)) {   // imageGradient, RendererUtil.h:566-620
+          const float* img = p.target_image + (size_t)view * p.W * p.H * 3;
+          float norm = 0.f;
+          for (int yy = -fs; yy <= fs; ++yy)
+            for (int xx = -fs; xx <= fs; ++xx) {
+              const V3 I = ldv3(img, (size_t)(y + yy) * p.W + (x + xx));
+              const float den = (float)(xx * xx + yy * yy);
+              float Gu = 0.f, Gv = 0.f;
+              if (den != 0.f) { Gu = (float)xx / den; Gv = (float)yy / den; }
+              dIu = dIu + Gu * I; dIv = dIv + Gv * I;
+              norm += fabsf(Gu);
+            }
+          dIu = v3(dIu.x / norm, dIu.y / norm, dIu.z / norm);
+          dIv = v3(dIv.x / norm, dIv.y / norm, dIv.z / norm);
+        }
+        const V3 gt = ldv3(p.target_grad, pix);
+        const float w0 = dot(gt, dIu), w1 = dot(gt, dIv);
+        // getJProjection (RendererUtil.h:275-332): d(K*E*[p;1] after divide)/dp at the fragment
+        const V3 fp = bc[0] * p0 + bc[1] * p1 + bc[2] * p2;
+        float M[3][4];   // K * E
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) M[r][c4] = cam.K[3 * r] * cam.E[c4] + cam.K[3 * r + 1] * cam.E[4 + c4] + cam.K[3 * r + 2] * cam.E[8 + c4];
+        const float Px = M[0][0] * fp.x + M[0][1] * fp.y + M[0][2] * fp.z + M[0][3];
+        const float Py = M[1][0] * fp.x + M[1][1] * fp.y + M[1][2] * fp.z + M[1][3];
+        const float Pz = M[2][0] * fp.x + M[2][1] * fp.y + M[2][2] * fp.z + M[2][3];
+        if (fabsf(Pz) > 0.0001f) {
+          const float iz = 1.f / Pz, kx = -Px / (Pz * Pz), ky = -Py / (Pz * Pz);
+          float w2[3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) w2[j] = w0 * (iz * M[0][j] + kx * M[2][j]) + w1 * (iz * M[1][j] + ky * M[2][j]);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) val[9 + i * 3 + j] += bc[i] * w2[j];
+        }
+      }
+    }
+
+    // ---- run-aggregated scatter: lane j owns value j ----
+    const int prevFace = __shfl_up_sync(FULL_MASK, face, 1);
+    const unsigned head = __ballot_sync(FULL_MASK, covered && (lane == 0 || prevFace != face));
+    const unsigned cont = (cv & ~head) >> 1;         // bit l: lane l+1 continues lane l's run
+    const unsigned endm = cv & ~cont;
+#pragma unroll
+    for (int j = 0; j < kVals; ++j) mybuf[lane * kVals + j] = val[j];
+    __syncwarp();
+    const int arr = lane / 9, vi = (lane % 9) / 3, comp = lane % 3;
+    const bool active = lane < kVals && ((arr == 0 && p.albedo == GVV_ALBEDO_VERTEX_COLOR) ||
+                                         (arr == 1 && (shaded || p.target_grad)) || (arr == 2 && shaded));
+    float* base = arr == 0 ? p.vcol_grad : (arr == 1 ? p.vpos_grad : p.gnorm);
+    base += (size_t)b * p.N * 3 + comp;
+    float acc = 0.f;
+    unsigned rem = cv;
+    while (rem) {
+      const int l = __ffs(rem) - 1;
+      rem &= rem - 1;
+      if (lane < kVals) acc += mybuf[l * kVals + lane];
+      if ((endm >> l) & 1u) {
+        const int fr = __shfl_sync(FULL_MASK, face, l);
+        if (active) {
+          const int4 fc = __ldg(p.faces4 + fr);
+          const int vid = vi == 0 ? fc.x : (vi == 1 ? fc.y : fc.z);
+          if (acc != 0.f) atomicAdd(base + (size_t)vid * 3, acc);
+        }
+        acc = 0.f;
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- SH gradient: warp -> block -> 27 atomics per block ----
+  float shsum = 0.f;
+  if (shaded && cv) {
+#pragma unroll
+    for (int j = 0; j < kVals; ++j) mybuf[lane * kVals + j] = shv[j];
+    __syncwarp();
+    if (lane < kVals) {
+      unsigned rem = cv;
+      while (rem) { const int l = __ffs(rem) - 1; rem &= rem - 1; shsum += mybuf[l * kVals + lane]; }
+    }
+  }
+  if (lane < kVals) shPart[warp][lane] = shsum;
+  __syncthreads();
+  if (shaded && tid < kVals) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += shPart[w][tid];
+    if (s != 0.f) atomicAdd(p.sh_grad + (size_t)view * 27 + tid, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+normal_term_kernel(const float* __restrict__ vertex_pos, const float* __restrict__ gnorm, const int4* __restrict__ faces4,
+                   const int* __restrict__ vfOffsets, const int* __restrict__ vfList, float* __restrict__ vpos_grad, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (n >= N) return;
+  const float* pos = vertex_pos + (size_t)b * N * 3;
+  const float* gn = gnorm + (size_t)b * N * 3;
+  V3 sum = v3(0.f, 0.f, 0.f);
+  const int beg = __ldg(vfOffsets + n), end = __ldg(vfOffsets + n + 1);
+  for (int i = beg; i < end; ++i) {
+    const int4 fc = __ldg(faces4 + __ldg(vfList + i));
+    V3 S = ldv3(gn, fc.x);
+    if (fc.y != fc.x) S = S + ldv3(gn, fc.y);
+    if (fc.z != fc.x && fc.z != fc.y) S = S + ldv3(gn, fc.z);
+    const V3 pi = ldv3(pos, fc.x), pj = ldv3(pos, fc.y), pk = ldv3(pos, fc.z);
+    const V3 e1 = pj - pi, e2 = pk - pi;
+    // S * J_vi = e1 x S - e2 x S ; S * J_vj = e2 x S ; S * J_vk = S x e1   (getJ_vi/vj/vk)
+    if (n == fc.x) sum = sum + (cross(e1, S) - cross(e2, S));
+    if (n == fc.y) sum = sum + cross(e2, S);
+    if (n == fc.z) sum = sum + cross(S, e1);
+  }
+  float* out = vpos_grad + ((size_t)b * N + n) * 3;
+  out[0] += sum.x; out[1] += sum.y; out[2] += sum.z;
+}
+
+// ------------------------------------------------------------------------------------------------
+int launch_camera(const float* extr, const float* intr, CamRec* cams, int* bigCount, int V, cudaStream_t st);
+
+int launch_backward(const BwdArgs& a, cudaStream_t st) {
+  const int V = a.B * a.C;
+  int launches = launch_camera(a.extrinsics, a.intrinsics, a.s.cams, nullptr, V, st);
+  ZeroArgs z;
+  const long long nv = (long long)a.B * a.N * 3;
+  z.p[0] = a.vpos_grad; z.n[0] = nv;
+  z.p[1] = a.vcol_grad; z.n[1] = nv;
+  z.p[2] = a.s.gnorm;   z.n[2] = nv;
+  z.p[3] = a.sh_grad;   z.n[3] = (long long)V * 27;
+  z.p[4] = a.tex_grad;  z.n[4] = a.tex_grad ? (long long)a.B * a.texH * a.texW * 3 : 0;
+  zero_kernel<<<148 * 8, 256, 0, st>>>(z);
+  ++launches;
+  PixelParams p;
+  p.render_grad = a.render_grad; p.target_grad = a.target_grad; p.vertex_pos = a.vertex_pos; p.vertex_color = a.vertex_color;
+  p.texture = a.texture; p.sh_coeff = a.sh_coeff; p.target_image = a.target_image; p.vertex_normal = a.vertex_normal;
+  p.bary = a.bary; p.texcoords = a.texcoords; p.face = a.face; p.faces4 = a.faces4; p.cams = a.s.cams;
+  p.vpos_grad = a.vpos_grad; p.vcol_grad = a.vcol_grad; p.tex_grad = a.tex_grad; p.sh_grad = a.sh_grad; p.gnorm = a.s.gnorm;
+  p.C = a.C; p.N = a.N; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
+  p.albedo = a.albedo; p.shading = a.shading; p.imgFilter = a.imgFilter;
+  pixel_grad_kernel<<<dim3((a.W + 31) / 32, (a.H + 7) / 8, V), 256, 0, st>>>(p);
+  ++launches;
+  if (a.shading == GVV_SHADING_SHADED) {
+    normal_term_kernel<<<dim3((a.N + 127) / 128, a.B), 128, 0, st>>>(a.vertex_pos, a.s.gnorm, a.faces4, a.vfOffsets, a.vfList,
+                                                                    a.vpos_grad, a.N);
+    ++launches;
+  }
+  return cudaGetLastError() == cudaSuccess ? launches : -1;
+}
+
+}  // namespace gvv

@@ -1,0 +1,529 @@
+// gvv_forward.cu -- forward pass of the rasteriser for sm_100a.
+//
+// Replaces the reference's eight per-batch-element launches (CUDABasedRasterization.cu:449-473)
+// by six launches that cover ALL batch elements and cameras at once:
+//
+//   camera_kernel     per view        E^-1, (K*E)^-1, ray origin            (ref :23-67)
+//   vertex_kernel     per (b, vertex) /1000 pre-scale, vertex normal via CSR, projection into
+//                                     every camera of b, colour repack       (ref :98-174)
+//   bin_count_kernel  per (view, tri) bbox (ref :184-208) -> tile histogram / big list
+//   bin_scan_kernel   per view        exclusive scan of the tile histogram
+//   bin_fill_kernel   per (view, tri) triangle ids into per-tile bins
+//   raster_kernel     per (view, tile) 64-bit (depth|id) z-tile in shared memory resolved with
+//                                     atomicMin semantics, then resolve + shade + write of all six
+//                                     outputs of the tile (ref :215-408, both raster passes and the
+//                                     28 B/px clear of initializeDevice :74-91 fused away)
+//
+// No global z-buffer exists: the z-tile lives in shared memory, so HBM sees only the compulsory
+// output stores (24 B/px) plus the (L2-resident) mesh reads.
+#include "gvv_internal.h"
+
+namespace gvv {
+
+#define FULL_MASK 0xffffffffu
+
+// ------------------------------------------------------------------------------------------------
+// camera_kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void camera_kernel(const float* __restrict__ extr, const float* __restrict__ intr,
+                              CamRec* __restrict__ cams, int* __restrict__ bigCount, int V) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  float K[9], E[12], Einv[16], Pinv[16];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) K[i] = intr[v * 9 + i];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) E[i] = extr[v * 12 + i];
+  camera_inverse_exact(K, E, Einv, Pinv);
+  CamRec& r = cams[v];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) r.K[i] = K[i];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) r.E[i] = E[i];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { r.Einv[i] = Einv[i]; r.Pinv[i] = Pinv[i]; }
+  // o = 4th column of E^-1, o /= o.w (CameraUtil.h:253-255); ros = o / 1000 (RendererUtil.h:32)
+  const float ox = __fdiv_rn(Einv[3], Einv[15]);
+  const float oy = __fdiv_rn(Einv[7], Einv[15]);
+  const float oz = __fdiv_rn(Einv[11], Einv[15]);
+  r.ro[0] = ox; r.ro[1] = oy; r.ro[2] = oz;
+  r.ros[0] = __fdiv_rn(ox, 1000.f); r.ros[1] = __fdiv_rn(oy, 1000.f); r.ros[2] = __fdiv_rn(oz, 1000.f);
+  if (bigCount) bigCount[v] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// vertex_kernel: one thread per (batch element, vertex)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ F3 ld3(const float* __restrict__ p, int i) {
+  return mk3(__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2));
+}
+
+__global__ void __launch_bounds__(128)
+vertex_kernel(const float* __restrict__ vertex_pos, const float* __restrict__ vertex_color,
+              const int4* __restrict__ faces4, const int* __restrict__ vfOffsets, const int* __restrict__ vfList,
+              const CamRec* __restrict__ cams, float4* __restrict__ proj, float4* __restrict__ vscaled,
+              float4* __restrict__ vnorm4, float4* __restrict__ vcol4, float* __restrict__ vertex_normal_out,
+              int N, int C) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (n >= N) return;
+  const float* pos = vertex_pos + (size_t)b * N * 3;
+  const F3 p = ld3(pos, n);
+  vscaled[(size_t)b * N + n] = make_float4(__fdiv_rn(p.x, 1000.f), __fdiv_rn(p.y, 1000.f), __fdiv_rn(p.z, 1000.f), 0.f);
+  if (vertex_color) {
+    const F3 col = ld3(vertex_color + (size_t)b * N * 3, n);
+    vcol4[(size_t)b * N + n] = make_float4(col.x, col.y, col.z, 0.f);
+  }
+  // vertex normal = sum of incident face normals in ascending face order (ref :122-174); the
+  // reference leaves vertices without faces uninitialised, we define them as 0.
+  F3 nrm = mk3(0.f, 0.f, 0.f);
+  const int beg = __ldg(vfOffsets + n), end = __ldg(vfOffsets + n + 1);
+  for (int i = beg; i < end; ++i) {
+    const int4 fc = __ldg(faces4 + __ldg(vfList + i));
+    const F3 a = ld3(pos, fc.x), bb = ld3(pos, fc.y), cc = ld3(pos, fc.z);
+    const F3 fn = cross3x(sub3(bb, a), sub3(cc, a));
+    if (i == beg) nrm = fn;
+    else nrm = mk3(__fadd_rn(nrm.x, fn.x), __fadd_rn(nrm.y, fn.y), __fadd_rn(nrm.z, fn.z));
+  }
+  vnorm4[(size_t)b * N + n] = make_float4(nrm.x, nrm.y, nrm.z, 0.f);
+  for (int c = 0; c < C; ++c) {
+    const int view = b * C + c;
+    float* vn = vertex_normal_out + ((size_t)view * N + n) * 3;
+    vn[0] = nrm.x; vn[1] = nrm.y; vn[2] = nrm.z;
+    const CamRec* cam = cams + view;
+    proj[(size_t)view * N + n] = project_exact(cam->K, cam->E, p.x, p.y, p.z);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// binning
+// ------------------------------------------------------------------------------------------------
+struct TileRange { int tx0, ty0, tx1, ty1, n; };
+
+__device__ __forceinline__ TileRange tile_range(const int4* __restrict__ faces4, const float4* __restrict__ projv,
+                                                int f, int W, int H, int tileShift) {
+  const int4 fc = __ldg(faces4 + f);
+  const int4 bb = bbox_exact(__ldg(projv + fc.x), __ldg(projv + fc.y), __ldg(projv + fc.z), W, H);
+  TileRange r;
+  r.n = 0;
+  if (bb.x > bb.z || bb.y > bb.w) { r.tx0 = r.ty0 = 0; r.tx1 = r.ty1 = -1; return r; }
+  r.tx0 = bb.x >> tileShift; r.tx1 = bb.z >> tileShift;
+  r.ty0 = bb.y >> tileShift; r.ty1 = bb.w >> tileShift;
+  r.n = (r.tx1 - r.tx0 + 1) * (r.ty1 - r.ty0 + 1);
+  return r;
+}
+
+template <bool SMEM_HIST>
+__global__ void __launch_bounds__(256)
+bin_count_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj, int* __restrict__ tileCount,
+                 int* __restrict__ bigCount, int* __restrict__ bigList, int F, int N, int W, int H, int tileShift,
+                 int tilesX, int nT) {
+  extern __shared__ int hist[];
+  const int view = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (SMEM_HIST) {
+    for (int i = threadIdx.x; i < nT; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+  }
+  if (f < F) {
+    const TileRange r = tile_range(faces4, proj + (size_t)view * N, f, W, H, tileShift);
+    if (r.n > kMaxSmallTiles) {
+      const int slot = atomicAdd(bigCount + view, 1);
+      bigList[(size_t)view * F + slot] = f;
+    } else if (r.n > 0) {
+      for (int ty = r.ty0; ty <= r.ty1; ++ty)
+        for (int tx = r.tx0; tx <= r.tx1; ++tx) {
+          if (SMEM_HIST) atomicAdd(&hist[ty * tilesX + tx], 1);
+          else atomicAdd(tileCount + (size_t)view * nT + ty * tilesX + tx, 1);
+        }
+    }
+  }
+  if (SMEM_HIST) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nT; i += blockDim.x) {
+      const int c = hist[i];
+      if (c) atomicAdd(tileCount + (size_t)view * nT + i, c);
+    }
+  }
+}
+
+// exclusive scan of one view's tile histogram (one block per view)
+__global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ tileCount, int* __restrict__ tileOffset, int nT) {
+  __shared__ int warpSum[32];
+  __shared__ int carry;
+  const int view = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nT; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = (i < nT) ? tileCount[(size_t)view * nT + i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL_MASK, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warpSum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warpSum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL_MASK, w, o); if (lane >= o) w += y; }
+      warpSum[lane] = w;
+    }
+    __syncthreads();
+    const int prefix = carry + (warp ? warpSum[warp - 1] : 0) + x - v;
+    if (i < nT) tileOffset[(size_t)view * nT + i] = prefix;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += warpSum[31];
+    __syncthreads();
+  }
+}
+
+template <bool SMEM_HIST>
+__global__ void __launch_bounds__(256)
+bin_fill_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj, const int* __restrict__ tileOffset,
+                int* __restrict__ tileCursor, int* __restrict__ bins, int F, int N, int W, int H, int tileShift,
+                int tilesX, int nT) {
+  extern __shared__ int sm[];   // SMEM_HIST: hist[nT] then base[nT]
+  int* hist = sm;
+  int* base = sm + nT;
+  const int view = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  TileRange r; r.n = 0; r.tx0 = r.ty0 = 0; r.tx1 = r.ty1 = -1;
+  if (f < F) r = tile_range(faces4, proj + (size_t)view * N, f, W, H, tileShift);
+  const bool small = r.n > 0 && r.n <= kMaxSmallTiles;
+  int* viewBins = bins + (size_t)view * F * kMaxSmallTiles;
+  const int* off = tileOffset + (size_t)view * nT;
+  int* cur = tileCursor + (size_t)view * nT;
+  if (SMEM_HIST) {
+    for (int i = threadIdx.x; i < nT; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    if (small)
+      for (int ty = r.ty0; ty <= r.ty1; ++ty)
+        for (int tx = r.tx0; tx <= r.tx1; ++tx) atomicAdd(&hist[ty * tilesX + tx], 1);
+    __syncthreads();
+    // one global reservation per tile this block touches
+    for (int i = threadIdx.x; i < nT; i += blockDim.x) {
+      const int c = hist[i];
+      if (c) { base[i] = off[i] + atomicAdd(cur + i, c); hist[i] = 0; }
+    }
+    __syncthreads();
+    if (small)
+      for (int ty = r.ty0; ty <= r.ty1; ++ty)
+        for (int tx = r.tx0; tx <= r.tx1; ++tx) {
+          const int t = ty * tilesX + tx;
+          viewBins[base[t] + atomicAdd(&hist[t], 1)] = f;
+        }
+  } else if (small) {
+    for (int ty = r.ty0; ty <= r.ty1; ++ty)
+      for (int tx = r.tx0; tx <= r.tx1; ++tx) {
+        const int t = ty * tilesX + tx;
+        viewBins[off[t] + atomicAdd(cur + t, 1)] = f;
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// raster_kernel
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) TriRec {   // 24 words; read back as six float4
+  float v0x, v0y, v0z, v1x;
+  float v1y, v1z, v2x, v2y;
+  float v2z, Nx, Ny, Nz;
+  float num, den, z0, z1;
+  float z2; int face; int start; int x0y0;
+  int w; int rcpw; int pad0; int pad1;
+};
+static_assert(sizeof(TriRec) == 96, "TriRec is 96 bytes");
+
+struct RasterParams {
+  const int4* faces4; const float4* proj; const float4* vscaled; const float4* vnorm4; const float4* vcol4;
+  const CamRec* cams;
+  int* tileCount; int* tileCursor; const int* tileOffset; const int* bigCount; const int* bigList; const int* bins;
+  const float* texture; const float* texcoords; const float* sh_coeff;
+  float* bary; int32_t* face; float* render;
+  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT;
+};
+
+__device__ __forceinline__ TriSetup load_setup(const RasterParams& p, int b, int view, int4 fc, F3 ros,
+                                               float& z0, float& z1, float& z2, int4* bb) {
+  const float4* vs = p.vscaled + (size_t)b * p.N;
+  const float4* pj = p.proj + (size_t)view * p.N;
+  const float4 s0 = __ldg(vs + fc.x), s1 = __ldg(vs + fc.y), s2 = __ldg(vs + fc.z);
+  const float4 p0 = __ldg(pj + fc.x), p1 = __ldg(pj + fc.y), p2 = __ldg(pj + fc.z);
+  z0 = p0.z; z1 = p1.z; z2 = p2.z;
+  if (bb) *bb = bbox_exact(p0, p1, p2, p.W, p.H);
+  return tri_setup_exact(mk3(s0.x, s0.y, s0.z), mk3(s1.x, s1.y, s1.z), mk3(s2.x, s2.y, s2.z), ros);
+}
+
+// spherical-harmonics irradiance * albedo: getShading (RendererUtil.h:135-173)
+__device__ __forceinline__ float sh_eval(const float* __restrict__ sh, F3 n) {
+  float s = sh[0];
+  s = __fmaf_rn(n.y, sh[1], s);
+  s = __fmaf_rn(n.z, sh[2], s);
+  s = __fmaf_rn(n.x, sh[3], s);
+  s = __fmaf_rn(__fmul_rn(n.x, n.y), sh[4], s);
+  s = __fmaf_rn(__fmul_rn(n.z, n.y), sh[5], s);
+  s = __fmaf_rn(__fmaf_rn(__fmul_rn(n.z, n.z), 3.f, -1.f), sh[6], s);
+  s = __fmaf_rn(__fmul_rn(n.x, n.z), sh[7], s);
+  s = __fmaf_rn(__fmaf_rn(n.x, n.x, -__fmul_rn(n.y, n.y)), sh[8], s);
+  return s;
+}
+
+template <int TS>
+__global__ void __launch_bounds__(256)
+raster_kernel(const RasterParams p) {
+  constexpr int NPIX = TS * TS;
+  constexpr int CHUNK = 256;
+  constexpr int SHIFT = 21;
+  __shared__ unsigned long long zt[NPIX];
+  __shared__ float rayx[NPIX], rayy[NPIX], rayz[NPIX];
+  __shared__ TriRec rec[CHUNK];
+  __shared__ int startArr[CHUNK + 40];
+  __shared__ int warpTot[8];
+  __shared__ float shc[27];
+  __shared__ CamRec cam;
+
+  const int tile = blockIdx.x, view = blockIdx.y;
+  const int b = view / p.C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tileX0 = (tile % p.tilesX) * TS, tileY0 = (tile / p.tilesX) * TS;
+  const size_t tidx = (size_t)view * p.nT + tile;
+  const int cntSmall = p.tileCount[tidx];
+  const int cntBig = p.bigCount[view];
+  const size_t pixBase = (size_t)view * p.W * p.H;
+
+  if (cntSmall == 0 && cntBig == 0) {
+    // empty tile: background only (face -1, bary 0, render (0,1,0): initializeDevice :80-89)
+    for (int q = tid; q < NPIX; q += 256) {
+      const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
+      if (x < p.W && y < p.H) {
+        const size_t pix = pixBase + (size_t)y * p.W + x;
+        p.face[pix] = -1;
+        reinterpret_cast<float2*>(p.bary)[pix] = make_float2(0.f, 0.f);
+        p.render[3 * pix + 0] = 0.f; p.render[3 * pix + 1] = 1.f; p.render[3 * pix + 2] = 0.f;
+      }
+    }
+    return;
+  }
+
+  if (tid < 64) reinterpret_cast<float*>(&cam)[tid] = reinterpret_cast<const float*>(p.cams + view)[tid];
+  if (tid >= 64 && tid < 64 + 27) shc[tid - 64] = p.sh_coeff[(size_t)view * 27 + (tid - 64)];
+  __syncthreads();
+  const F3 ros = mk3(cam.ros[0], cam.ros[1], cam.ros[2]);
+
+  // z-tile clear + per-pixel ray cache (the ray depends on pixel and camera only)
+  for (int q = tid; q < NPIX; q += 256) {
+    zt[q] = kEmptyKey;
+    const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
+    const F3 rd = ray_dir_exact(cam.Pinv, cam.ro, __fadd_rn((float)x, 0.5f), __fadd_rn((float)y, 0.5f));
+    rayx[q] = rd.x; rayy[q] = rd.y; rayz[q] = rd.z;
+  }
+
+  // ---- rasterise: the tile's own bin, then the view's big-triangle list ----
+  for (int pass = 0; pass < 2; ++pass) {
+    const int cnt = pass == 0 ? cntSmall : cntBig;
+    const int* list = pass == 0 ? p.bins + (size_t)view * p.F * kMaxSmallTiles + p.tileOffset[tidx]
+                                : p.bigList + (size_t)view * p.F;
+    for (int chunk = 0; chunk < cnt; chunk += CHUNK) {
+      __syncthreads();   // rec/startArr of the previous chunk (and the z-tile clear) are done
+      const int i = chunk + tid;
+      int n = 0;
+      TriRec mine;
+      if (i < cnt) {
+        const int f = __ldg(list + i);
+        const int4 fc = __ldg(p.faces4 + f);
+        float z0, z1, z2; int4 bb;
+        const TriSetup ts = load_setup(p, b, view, fc, ros, z0, z1, z2, &bb);
+        const int cx0 = max(bb.x, tileX0), cx1 = min(bb.z, tileX0 + TS - 1);
+        const int cy0 = max(bb.y, tileY0), cy1 = min(bb.w, tileY0 + TS - 1);
+        const int w = cx1 - cx0 + 1, h = cy1 - cy0 + 1;
+        if (w > 0 && h > 0) {
+          n = w * h;
+          mine.v0x = ts.v0.x; mine.v0y = ts.v0.y; mine.v0z = ts.v0.z;
+          mine.v1x = ts.v1.x; mine.v1y = ts.v1.y; mine.v1z = ts.v1.z;
+          mine.v2x = ts.v2.x; mine.v2y = ts.v2.y; mine.v2z = ts.v2.z;
+          mine.Nx = ts.N.x; mine.Ny = ts.N.y; mine.Nz = ts.N.z;
+          mine.num = ts.num; mine.den = ts.den; mine.z0 = z0; mine.z1 = z1; mine.z2 = z2;
+          mine.face = f; mine.x0y0 = (cx0 - tileX0) | ((cy0 - tileY0) << 16);
+          mine.w = w; mine.rcpw = ((1 << 18) + w - 1) / w; mine.pad0 = 0; mine.pad1 = 0;
+        }
+      }
+      // block-wide exclusive scan of (1 << SHIFT | n): rank among non-empty triangles + first fragment
+      const int packed = n > 0 ? ((1 << SHIFT) | n) : 0;
+      int x = packed;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL_MASK, x, o); if (lane >= o) x += y; }
+      if (lane == 31) warpTot[warp] = x;
+      __syncthreads();
+      int before = 0, total = 0;
+#pragma unroll
+      for (int wi = 0; wi < 8; ++wi) { const int t = warpTot[wi]; if (wi < warp) before += t; total += t; }
+      const int excl = before + x - packed;
+      const int ntri = total >> SHIFT, nfrag = total & ((1 << SHIFT) - 1);
+      if (n > 0) {
+        const int rank = excl >> SHIFT;
+        mine.start = excl & ((1 << SHIFT) - 1);
+        rec[rank] = mine;
+        startArr[rank] = mine.start;
+      }
+      if (tid < 40) startArr[ntri + tid] = 0x7fffffff;
+      __syncthreads();
+      if (nfrag == 0) continue;
+
+      // fragments [0, nfrag) are split evenly over the 8 warps (32-aligned), whatever the triangle sizes
+      const int per = ((nfrag + 7) / 8 + 31) & ~31;
+      const int lo = warp * per, hi = min(lo + per, nfrag);
+      if (lo < hi) {
+        int c0 = 0;
+        for (int j = lane; j < ntri; j += 32) c0 += (startArr[j] <= lo) ? 1 : 0;
+        int K0 = __reduce_add_sync(FULL_MASK, c0) - 1;   // triangle containing fragment `lo`
+        for (int fb = lo; fb < hi; fb += 32) {
+          const int s = startArr[K0 + 1 + lane];
+          const unsigned bits = (s < fb + 32) ? (1u << (s - fb)) : 0u;
+          const unsigned mask = __reduce_or_sync(FULL_MASK, bits);
+          const int k = K0 + __popc(mask & ((2u << lane) - 1u));
+          K0 += __popc(mask);
+          const int fr = fb + lane;
+          if (fr < hi) {
+            const float4* rp = reinterpret_cast<const float4*>(&rec[k]);
+            const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3];
+            const int4 r4 = reinterpret_cast<const int4*>(rp)[4];
+            const int4 r5 = reinterpret_cast<const int4*>(rp)[5];
+            const int local = fr - r4.z;
+            const int dy = (int)(((unsigned)local * (unsigned)r5.y) >> 18);
+            const int dx = local - dy * r5.x;
+            const int q = ((r4.w >> 16) + dy) * TS + (r4.w & 0xffff) + dx;
+            TriSetup ts;
+            ts.v0 = mk3(r0.x, r0.y, r0.z); ts.v1 = mk3(r0.w, r1.x, r1.y); ts.v2 = mk3(r1.z, r1.w, r2.x);
+            ts.N = mk3(r2.y, r2.z, r2.w); ts.num = r3.x; ts.den = r3.y;
+            const F3 rd = mk3(rayx[q], rayy[q], rayz[q]);
+            float a, bq, c;
+            if (hit_exact(ts, ros, rd, a, bq, c)) {
+              const int depth = depth_key_exact(a, bq, c, r3.z, r3.w, __int_as_float(r4.x));
+              const unsigned long long key = pack_key(depth, r4.y);
+              unsigned long long cur = zt[q];
+              while (key < cur) {                     // 64-bit atomicMin on the shared z-tile
+                const unsigned long long old = atomicCAS(&zt[q], cur, key);
+                if (old == cur) break;
+                cur = old;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- resolve + shade + write (ref pass 2, :286-403) ----
+  const float4* vn = p.vnorm4 + (size_t)b * p.N;
+  const float4* vc = p.vcol4 + (size_t)b * p.N;
+  const bool doShade = (p.shading == GVV_SHADING_SHADED && p.albedo != GVV_ALBEDO_NORMAL) || p.albedo == GVV_ALBEDO_LIGHTING;
+  for (int q = tid; q < NPIX; q += 256) {
+    const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
+    if (x >= p.W || y >= p.H) continue;
+    const size_t pix = pixBase + (size_t)y * p.W + x;
+    const unsigned long long key = zt[q];
+    int faceId = -1;
+    float a = 0.f, bq = 0.f, cr = 0.f, cg = 1.f, cb = 0.f;
+    if (key != kEmptyKey) {
+      faceId = (int)(unsigned)(key & 0xffffffffull);
+      const int4 fc = __ldg(p.faces4 + faceId);
+      float z0, z1, z2, c;
+      const TriSetup ts = load_setup(p, b, view, fc, ros, z0, z1, z2, nullptr);
+      const F3 rd = mk3(rayx[q], rayy[q], rayz[q]);
+      hit_exact(ts, ros, rd, a, bq, c);   // same arithmetic as the rasterising pass => same (a,b,c)
+      const float4 n0 = __ldg(vn + fc.x), n1 = __ldg(vn + fc.y), n2 = __ldg(vn + fc.z);
+      F3 nr = mk3(interp3(a, bq, c, n0.x, n1.x, n2.x), interp3(a, bq, c, n0.y, n1.y, n2.y), interp3(a, bq, c, n0.z, n1.z, n2.z));
+      const float len = __fsqrt_rn(dot3x(nr, nr));
+      nr = mk3(__fdiv_rn(nr.x, len), __fdiv_rn(nr.y, len), __fdiv_rn(nr.z, len));
+      if (dot3x(nr, rd) > 0.f) nr = mk3(-nr.x, -nr.y, -nr.z);
+      if (p.albedo == GVV_ALBEDO_TEXTURED) {
+        const float* tc = p.texcoords + (size_t)faceId * 6;
+        const float u = interp3(a, bq, c, __ldg(tc + 0), __ldg(tc + 2), __ldg(tc + 4));
+        const float v = interp3(a, bq, c, __fsub_rn(1.f, __ldg(tc + 1)), __fsub_rn(1.f, __ldg(tc + 3)), __fsub_rn(1.f, __ldg(tc + 5)));
+        const float fu = fminf(fmaxf(__fmul_rn(u, (float)p.texW), 0.f), (float)(p.texW - 1));
+        const float fv = fminf(fmaxf(__fmul_rn(v, (float)p.texH), 0.f), (float)(p.texH - 1));
+        // nearest texel (LU,LV); the bilinear mix is commented out in the reference (:372-373)
+        const int iu = __float2int_rz(__fadd_rn((float)__float2int_rz(__fadd_rn(fu, -0.5f)), 0.5f));
+        const int iv = __float2int_rz(__fadd_rn((float)__float2int_rz(__fadd_rn(fv, -0.5f)), 0.5f));
+        const float* tx = p.texture + ((size_t)b * p.texH * p.texW + (size_t)iv * p.texW + iu) * 3;
+        cr = __ldg(tx); cg = __ldg(tx + 1); cb = __ldg(tx + 2);
+      } else if (p.albedo == GVV_ALBEDO_VERTEX_COLOR) {
+        const float4 c0 = __ldg(vc + fc.x), c1 = __ldg(vc + fc.y), c2 = __ldg(vc + fc.z);
+        cr = interp3(a, bq, c, c0.x, c1.x, c2.x);
+        cg = interp3(a, bq, c, c0.y, c1.y, c2.y);
+        cb = interp3(a, bq, c, c0.z, c1.z, c2.z);
+      } else if (p.albedo == GVV_ALBEDO_NORMAL) {
+        cr = __fmul_rn(__fadd_rn(nr.x, 1.f), 0.5f);
+        cg = __fmul_rn(__fadd_rn(nr.y, 1.f), 0.5f);
+        cb = __fmul_rn(__fadd_rn(nr.z, 1.f), 0.5f);
+      } else {
+        cr = cg = cb = 1.f;   // lighting / foregroundMask
+      }
+      if (doShade) {
+        cr = __fmul_rn(cr, sh_eval(shc, nr));
+        cg = __fmul_rn(cg, sh_eval(shc + 9, nr));
+        cb = __fmul_rn(cb, sh_eval(shc + 18, nr));
+      }
+    }
+    p.face[pix] = faceId;
+    reinterpret_cast<float2*>(p.bary)[pix] = make_float2(a, bq);
+    p.render[3 * pix + 0] = cr; p.render[3 * pix + 1] = cg; p.render[3 * pix + 2] = cb;
+  }
+  if (tid == 0) { p.tileCount[tidx] = 0; p.tileCursor[tidx] = 0; }   // self-cleaning scratch
+}
+
+// ------------------------------------------------------------------------------------------------
+// launcher
+// ------------------------------------------------------------------------------------------------
+static inline bool launch_ok() { return cudaGetLastError() == cudaSuccess; }
+
+int launch_camera(const float* extr, const float* intr, CamRec* cams, int* bigCount, int V, cudaStream_t st) {
+  camera_kernel<<<(V + 63) / 64, 64, 0, st>>>(extr, intr, cams, bigCount, V);
+  return 1;
+}
+
+int launch_forward(const FwdArgs& a, cudaStream_t st) {
+  const int V = a.B * a.C;
+  int launches = launch_camera(a.extrinsics, a.intrinsics, a.s.cams, a.s.bigCount, V, st);
+  vertex_kernel<<<dim3((a.N + 127) / 128, a.B), 128, 0, st>>>(a.vertex_pos, a.vertex_color, a.faces4, a.vfOffsets, a.vfList,
+                                                             a.s.cams, a.s.proj, a.s.vscaled, a.s.vnorm4, a.s.vcol4,
+                                                             a.vertex_normal, a.N, a.C);
+  ++launches;
+  const int tileShift = a.tile == 32 ? 5 : 4;
+  const dim3 gridF((a.F + 255) / 256, V);
+  if (a.nT <= kSmemHistTiles) {
+    bin_count_kernel<true><<<gridF, 256, a.nT * sizeof(int), st>>>(a.faces4, a.s.proj, a.s.tileCount, a.s.bigCount, a.s.bigList,
+                                                                  a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
+  } else {
+    bin_count_kernel<false><<<gridF, 256, 0, st>>>(a.faces4, a.s.proj, a.s.tileCount, a.s.bigCount, a.s.bigList,
+                                                  a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
+  }
+  ++launches;
+  bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.nT);
+  ++launches;
+  if (a.nT <= kSmemHistTiles) {
+    bin_fill_kernel<true><<<gridF, 256, 2 * a.nT * sizeof(int), st>>>(a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCursor, a.s.bins,
+                                                                     a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
+  } else {
+    bin_fill_kernel<false><<<gridF, 256, 0, st>>>(a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCursor, a.s.bins,
+                                                 a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
+  }
+  ++launches;
+  RasterParams p;
+  p.faces4 = a.faces4; p.proj = a.s.proj; p.vscaled = a.s.vscaled; p.vnorm4 = a.s.vnorm4; p.vcol4 = a.s.vcol4;
+  p.cams = a.s.cams; p.tileCount = a.s.tileCount; p.tileCursor = a.s.tileCursor; p.tileOffset = a.s.tileOffset;
+  p.bigCount = a.s.bigCount; p.bigList = a.s.bigList; p.bins = a.s.bins;
+  p.texture = a.texture; p.texcoords = a.texcoords; p.sh_coeff = a.sh_coeff;
+  p.bary = a.bary; p.face = a.face; p.render = a.render;
+  p.C = a.C; p.N = a.N; p.F = a.F; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
+  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT;
+  const dim3 gridT(a.nT, V);
+  if (a.tile == 16) raster_kernel<16><<<gridT, 256, 0, st>>>(p);
+  else raster_kernel<32><<<gridT, 256, 0, st>>>(p);
+  ++launches;
+  return launch_ok() ? launches : -1;
+}
+
+}  // namespace gvv

@@ -1,0 +1,80 @@
+// gvv_internal.h -- handle layout and launcher declarations shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gvv_exact.cuh"
+#include "../../include/gvv_b200.h"
+
+namespace gvv {
+
+// A triangle whose bbox overlaps more than kMaxSmallTiles tiles goes to the per-view "big" list,
+// which every tile of that view scans; everything else is appended to per-tile bins.  This bounds
+// the bin pool by F*kMaxSmallTiles entries per view without ever reading a count back to the host.
+constexpr int kMaxSmallTiles = 16;
+constexpr int kSmemHistTiles = 4096;   // largest tile grid handled with a shared-memory histogram
+
+struct Scratch {
+  int capViews = 0, capBatch = 0;
+  CamRec* cams = nullptr;        // [V]
+  float4* proj = nullptr;        // [V*N]  (x/z, y/z, z, 0)
+  float4* vscaled = nullptr;     // [B*N]  vertex / 1000 (div.rn), w = 0
+  float4* vnorm4 = nullptr;      // [B*N]  unnormalised vertex normal
+  float4* vcol4 = nullptr;       // [B*N]  vertex colour
+  int* tileCount = nullptr;      // [V*nT] self-cleaning (the raster kernel zeroes its own entry)
+  int* tileCursor = nullptr;     // [V*nT] self-cleaning
+  int* tileOffset = nullptr;     // [V*nT]
+  int* bigCount = nullptr;       // [V]    zeroed by camera_kernel of the next call
+  int* bigList = nullptr;        // [V*F]
+  int* bins = nullptr;           // [V*F*kMaxSmallTiles]
+  float* gnorm = nullptr;        // [B*N*3] backward: dL/d(unnormalised vertex normal)
+};
+
+}  // namespace gvv
+
+struct gvv_renderer {
+  int device = 0;
+  int F = 0, N = 0, C = 0, W = 0, H = 0;
+  int albedo = 0, shading = 0, imgFilter = 1, texFilter = 1, computeNormalMap = 0;
+  int tile = 32, tilesX = 0, tilesY = 0, nT = 0;
+  bool hasTexcoords = false;
+  int4* faces4 = nullptr;     // [F] (v0,v1,v2,0)
+  float* texcoords = nullptr; // [F*6]
+  int* vfOffsets = nullptr;   // [N+1]  vertex -> incident faces (ascending face id), CSR
+  int* vfList = nullptr;      // [vfOffsets[N]]
+  // UV-space (face, a, b, c) table for compute_normal_map, built lazily per texture size
+  float4* texelTable = nullptr; int tableH = 0, tableW = 0;
+  gvv::Scratch s;
+  int64_t launches = 0;
+};
+
+namespace gvv {
+
+struct FwdArgs {
+  int B, C, N, F, W, H, texH, texW, albedo, shading;
+  int tile, tilesX, tilesY, nT;
+  const float *vertex_pos, *vertex_color, *texture, *sh_coeff, *extrinsics, *intrinsics;
+  const float* texcoords;
+  const int4* faces4;
+  const int *vfOffsets, *vfList;
+  float* bary; int32_t* face; float* render; float* vertex_normal;
+  Scratch s;
+};
+
+struct BwdArgs {
+  int B, C, N, F, W, H, texH, texW, albedo, shading, imgFilter;
+  const float *render_grad, *target_grad, *vertex_pos, *vertex_color, *texture, *sh_coeff, *target_image,
+      *vertex_normal, *bary, *extrinsics, *intrinsics, *texcoords;
+  const int32_t* face;
+  const int4* faces4;
+  const int *vfOffsets, *vfList;
+  float *vpos_grad, *vcol_grad, *tex_grad, *sh_grad;
+  Scratch s;
+};
+
+// Each returns the number of kernels launched, or -1 after a launch error.
+int launch_forward(const FwdArgs& a, cudaStream_t st);
+int launch_normal_map(const FwdArgs& a, const float4* texelTable, float* normal_map, cudaStream_t st);
+int launch_backward(const BwdArgs& a, cudaStream_t st);
+int launch_build_texel_table(const float* texcoords, int F, int texH, int texW, float4* table, cudaStream_t st);
+
+}  // namespace gvv

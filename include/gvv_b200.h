@@ -1,0 +1,144 @@
+/*
+ * gvv_b200.h -- C ABI of the B200-native differentiable rasteriser.
+ *
+ * Drop-in boundary for the one hot path of ayushtewari/GVV-Differentiable-CUDA-Renderer:
+ * the TensorFlow custom ops `CudaRendererGpu` / `CudaRendererGradGpu`.  Every entry point
+ * below replaces one piece of the reference's op boundary (file:line are relative to the
+ * reference checkout):
+ *
+ *   gvv_create    <- CudaRenderer::CudaRenderer(OpKernelConstruction*)       cpp/src/TensorflowOperators/CudaRenderer/CudaRenderer.cpp:37-155
+ *                    + CUDABasedRasterization ctor (topology upload, CSR)    cpp/src/Renderer/CUDABasedRasterization.cpp:11-106,125-154
+ *                    + CudaRendererGrad ctor / CUDABasedRasterizationGrad    cpp/src/TensorflowOperators/CudaRenderer/CudaRendererGrad.cpp:43-101
+ *   gvv_forward   <- CudaRenderer::Compute (per-batch host loop)             CudaRenderer.cpp:298-335, op signature :5-33
+ *                    -> renderBuffersGPU                                     cpp/src/Renderer/CUDABasedRasterization.cu:449-473
+ *   gvv_backward  <- CudaRendererGrad::Compute                               CudaRendererGrad.cpp:252-292, op signature :6-39
+ *                    -> renderBuffersGradGPU                                 cpp/src/Renderer/CUDABasedRasterizationGrad.cu:624-635
+ *   gvv_destroy   <- ~CUDABasedRasterization / ~CUDABasedRasterizationGrad   CUDABasedRasterization.cpp:110-121
+ *   gvv_last_error<- replaces cutilSafeCall -> exit(-1)                      cpp/thirdParty/Shared/cutil/inc/cutil_inline_runtime.h:278-285
+ *
+ * Conventions
+ *   - plain C, no torch / TF types; all tensors are dense row-major fp32 (int32 for faces
+ *     and the face buffer) exactly as the reference op lays them out;
+ *   - every pointer passed to gvv_forward / gvv_backward is a DEVICE pointer on the device
+ *     the handle was created for; the caller owns all of them;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream); the calls never synchronise the host and never allocate once the scratch for
+ *     the largest batch seen so far exists;
+ *   - a handle is not re-entrant (same as one TF kernel instance);
+ *   - return value 0 = success; otherwise a GVV_E* code and gvv_last_error() (thread-local)
+ *     describes it.  The library never calls exit() and never throws across the ABI.
+ */
+#ifndef GVV_B200_H
+#define GVV_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* albedo_mode / shading_mode: same order as the reference enums
+ * (cpp/src/Renderer/CUDABasedRasterizationInput.h:25-35). */
+enum gvv_albedo_mode {
+  GVV_ALBEDO_VERTEX_COLOR    = 0,  /* "vertexColor"    */
+  GVV_ALBEDO_TEXTURED        = 1,  /* "textured"       */
+  GVV_ALBEDO_NORMAL          = 2,  /* "normal"         */
+  GVV_ALBEDO_LIGHTING        = 3,  /* "lighting"       */
+  GVV_ALBEDO_FOREGROUND_MASK = 4   /* "foregroundMask" (forces shadeless, CudaRenderer.cpp:72-76) */
+};
+enum gvv_shading_mode {
+  GVV_SHADING_SHADED    = 0,       /* "shaded"    */
+  GVV_SHADING_SHADELESS = 1        /* "shadeless" */
+};
+
+enum gvv_status {
+  GVV_OK = 0,
+  GVV_EINVAL = 1,     /* bad argument (the reference's OP_REQUIRES / silent early returns) */
+  GVV_ECUDA = 2,      /* a CUDA runtime call failed */
+  GVV_ENOMEM = 3,     /* scratch allocation failed */
+  GVV_EUNSUPPORTED = 4
+};
+
+/* Attributes of the op (CudaRenderer.cpp:23-33).  `faces` / `texcoords` are HOST pointers,
+ * copied at create time. */
+typedef struct gvv_desc {
+  const int32_t* faces;          /* [num_faces*3] vertex indices                        (attr faces)               */
+  int32_t        num_faces;
+  const float*   texcoords;      /* [num_faces*3*2] per-corner (u,v); may be NULL       (attr texture_coordinates) */
+  int32_t        num_vertices;   /*                                                      (attr number_of_vertices)  */
+  int32_t        num_cameras;    /*                                                      (attr number_of_cameras)   */
+  int32_t        width;          /* render_resolution_u                                                             */
+  int32_t        height;         /* render_resolution_v                                                             */
+  int32_t        albedo_mode;    /* enum gvv_albedo_mode                                                            */
+  int32_t        shading_mode;   /* enum gvv_shading_mode                                                           */
+  int32_t        image_filter_size;    /* half-width of the target-image gradient filter (backward, B8)             */
+  int32_t        texture_filter_size;  /* accepted and ignored, as in the reference's live code                     */
+  int32_t        compute_normal_map;   /* 1: UV-space normal map INSTEAD of rasterisation (CUDABasedRasterization.cu:463-466) */
+  int32_t        device;         /* CUDA device ordinal                                                             */
+} gvv_desc;
+
+typedef struct gvv_renderer* gvv_handle;
+
+int gvv_create(const gvv_desc* desc, gvv_handle* out);
+int gvv_destroy(gvv_handle h);
+
+/* Forward: inputs in0..in6 and outputs out0..out5 of CudaRendererGpu (CudaRenderer.cpp:5-21).
+ *   vertex_pos   [B,N,3]   vertex_color [B,N,3]   texture [B,texH,texW,3]   sh_coeff [B,C,27]
+ *   target_image [B,C,H,W,3] (may be NULL together with target_image_out)
+ *   extrinsics   [B,C*12]  intrinsics   [B,C*9]
+ *   barycentric_buffer [B,C,H,W,2]   face_buffer int32 [B,C,H,W]   render_buffer [B,C,H,W,3]
+ *   vertex_normal [B,C,N,3]   target_image_out [B,C,H,W,3] (copy of target_image; skipped when
+ *   it aliases target_image or is NULL)   normal_map [B,texH,texW,3] (written only when
+ *   compute_normal_map; may be NULL otherwise) */
+int gvv_forward(gvv_handle h, int32_t batch, int32_t tex_h, int32_t tex_w,
+                const float* vertex_pos, const float* vertex_color, const float* texture,
+                const float* sh_coeff, const float* target_image,
+                const float* extrinsics, const float* intrinsics,
+                float* barycentric_buffer, int32_t* face_buffer, float* render_buffer,
+                float* vertex_normal, float* target_image_out, float* normal_map,
+                void* stream);
+
+/* Backward: inputs and outputs of CudaRendererGradGpu (CudaRendererGrad.cpp:6-28).
+ *   render_buffer_grad [B,C,H,W,3]; target_buffer_grad [B,C,H,W,3] or NULL (= all zeros: the
+ *   model-to-data term B8 is skipped); the rest as in gvv_forward.
+ *   Outputs (overwritten, not accumulated): vertex_pos_grad [B,N,3], vertex_color_grad [B,N,3],
+ *   texture_grad [B,texH,texW,3], sh_coeff_grad [B,C,27]. */
+int gvv_backward(gvv_handle h, int32_t batch, int32_t tex_h, int32_t tex_w,
+                 const float* render_buffer_grad,
+                 const float* vertex_pos, const float* vertex_color, const float* texture,
+                 const float* sh_coeff, const float* target_image, const float* vertex_normal,
+                 const float* barycentric_buffer, const int32_t* face_buffer,
+                 const float* target_buffer_grad,
+                 const float* extrinsics, const float* intrinsics,
+                 float* vertex_pos_grad, float* vertex_color_grad, float* texture_grad,
+                 float* sh_coeff_grad,
+                 void* stream);
+
+const char* gvv_last_error(void);
+
+/* ---- diagnostics (not part of the reference boundary) ------------------------------------ */
+
+/* Number of kernels the library launched on behalf of this handle since creation. */
+int64_t gvv_launch_count(gvv_handle h);
+
+/* Copies an internal buffer of the LAST forward call to host memory (synchronises `stream`).
+ * which: 0 = per-view camera records (64 floats each: K[9] E[12] Einv[16] Pinv[16] ro[3] ros[3] pad),
+ *        1 = projected vertices float4[V*N] (x/z, y/z, z, 0).
+ * Returns the number of bytes the buffer holds (copies min(bytes, capacity)). */
+int64_t gvv_debug_copy(gvv_handle h, int32_t which, void* host_dst, int64_t capacity, void* stream);
+
+/* Runtime knobs: key "tile" (16|32 rasteriser tile edge; default 32). Returns 0 on success. */
+int gvv_set_option(gvv_handle h, const char* key, int32_t value);
+
+/* Atomic-throughput micro-benchmark used for the roofline denominators:
+ * kind 0: red.global.min.u64 over `n_addr` 64-bit words, kind 1: red.global.add.f32 over
+ * `n_addr` floats; `n_ops` operations with pseudo-random addresses, one per thread.
+ * Returns operations per second through *ops_per_s (device-timed with CUDA events). */
+int gvv_bench_atomics(int32_t device, int32_t kind, int64_t n_addr, int64_t n_ops, int32_t iters,
+                      double* ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVV_B200_H */
