@@ -1,0 +1,330 @@
+#!/usr/bin/env python3
+"""bench.py -- views/sec, forward + backward, of the rasteriser hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): synthetic UV sphere, ~35k vertices / ~70k
+triangles, 8 ring cameras at 1024x1024, ~50 % coverage, vertexColor + shaded, gradients w.r.t.
+vertex positions, colours and SH; one batch element (8 views) per GPU per step ("weak" scaling).
+A step = gvv_forward + gvv_backward over that batch.  With N > 1 the SH coefficients and vertex
+colours are treated as shared across the batch, so each step ends with ONE NCCL all-reduce of
+their gradients (sharding.allreduce_shared_grads); nothing else crosses GPUs.
+
+One JSON line on stdout (rank 0).  `value` = kernels only, inputs resident in HBM; `e2e` = the same
+step through the public Python API (CudaRendererGpu + autograd) with per-step host->device copies
+of the step's variable inputs from pinned memory and device->host reads of loss and gradients.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BASE = json.load(open(os.path.join(ROOT, "BASELINE.json"))) if os.path.exists(os.path.join(ROOT, "BASELINE.json")) else {}
+METRIC = BASE.get("metric", "views/sec fwd+bwd at 1024^2, 70k tris")
+UNIT = "views/s"
+WORKLOAD = dict(rings=187, segments=188, cameras=8, width=1024, height=1024, tex=64)
+INPUT_KEYS = ("vertex_pos", "vertex_color", "texture", "sh_coeff", "target_image", "extrinsics", "intrinsics")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(rank):
+    from gvv_differentiable_cuda_renderer_b200 import synthetic
+    sc = synthetic.make_scene(kind="sphere", batch=1, seed=0, **WORKLOAD)
+    if rank:   # every rank renders its own batch element: same topology, different vertex noise
+        rng = np.random.default_rng(100 + rank)
+        sc["vertex_pos"] = (sc["vertex_pos"] + rng.normal(0, 0.3, sc["vertex_pos"].shape)).astype(np.float32)
+    return sc
+
+
+def algorithmic_bytes(sc):
+    """compulsory traffic per view (z-buffer, bins, clears are NOT counted)."""
+    P, N, F = sc["width"] * sc["height"], sc["num_vertices"], len(sc["faces"])
+    fwd = P * 24 + N * 36 + F * 12
+    bwd = P * 24 + N * 60 + F * 12 + 216
+    per_kernel = {"raster_kernel": P * 24 + N * 24 + F * 12, "pixel_grad_kernel": P * 24 + N * 48 + F * 12 + 216}
+    return fwd, bwd, per_kernel
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from gvv_differentiable_cuda_renderer_b200 import CudaRendererGpu, _native, sharding
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the renderer has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sc = make_inputs(rank)
+    N, C, W, H = sc["num_vertices"], sc["num_cameras"], sc["width"], sc["height"]
+    V = C   # views per step per GPU (B = 1)
+    ins = [torch.as_tensor(sc[k], device=dev) for k in INPUT_KEYS]
+    G = torch.randn((1, C, H, W, 3), generator=torch.Generator().manual_seed(3)).to(dev)   # render_buffer_grad ~ N(0,1) seed 3
+    r = _native.NativeRenderer(sc["faces"], sc["texcoords"], N, C, W, H, "vertexColor", "shaded", 1, 1, False, dev)
+    if args.tile:
+        r.set_option("tile", args.tile)
+
+    def step():
+        bary, face, render, vn, _, _ = r.forward(*ins)
+        gpos, gcol, gtex, gsh = r.backward(G, None, ins[0], ins[1], ins[2], ins[3], ins[4], vn, bary, face, ins[5], ins[6])
+        if world > 1:
+            sharding.allreduce_shared_grads([gsh, gcol])
+        return gpos
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    l0 = r.launch_count
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms = timed(step, args.steps)
+    launches = r.launch_count - l0
+    clocks = sampler.stop() if sampler else None
+    value = world * V * args.steps / (ms * 1e-3)
+
+    # per-kernel device time (CUDA events on the launching stream) over another K steps
+    r.set_option("time_kernels", 1)
+    timed(step, args.steps)
+    kt = r.kernel_times()
+    r.set_option("time_kernels", 0)
+    fwd_b, bwd_b, per_kernel = algorithmic_bytes(sc)
+    peak, peak_src = peaks()
+    dom = max((k for k in kt if k in per_kernel), key=lambda k: kt[k][0])
+    dom_ms = kt[dom][0] / kt[dom][1]
+    achieved = per_kernel[dom] * V / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
+                "kernel_ms_per_launch": round(dom_ms, 4), "algorithmic_bytes_per_launch": per_kernel[dom] * V,
+                "step_hbm_frac": round((fwd_b + bwd_b) * V / (ms / args.steps * 1e-3) / 1e9 / peak, 5),
+                "kernel_ms_per_step": {k: round(v[0] / max(1, args.steps), 4) for k, v in sorted(kt.items())}}
+
+    # ---- e2e: public Python API, host buffers in pinned memory ----
+    host = {k: torch.as_tensor(sc[k]).pin_memory() for k in ("vertex_pos", "vertex_color", "sh_coeff", "extrinsics", "intrinsics")}
+    faces_l, tcs_l = sc["faces"].reshape(-1), sc["texcoords"].reshape(-1)
+    out_host = {k: torch.empty_like(host[k]).pin_memory() for k in ("vertex_pos", "vertex_color", "sh_coeff")}
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * 4 for t in host.values())
+    d2h = sum(t.numel() * 4 for t in out_host.values()) + 4
+
+    def e2e_step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        for k in ("vertex_pos", "vertex_color", "sh_coeff"):
+            d[k].requires_grad_(True)
+        layer = CudaRendererGpu(faces_attr=faces_l, texCoords_attr=tcs_l, numberOfVertices_attr=N, numberOfCameras_attr=C,
+                                renderResolutionU_attr=W, renderResolutionV_attr=H, albedoMode_attr="vertexColor",
+                                shadingMode_attr="shaded", vertexPos_input=d["vertex_pos"], vertexColor_input=d["vertex_color"],
+                                texture_input=ins[2], shCoeff_input=d["sh_coeff"], targetImage_input=ins[4],
+                                extrinsics_input=d["extrinsics"], intrinsics_input=d["intrinsics"], device=dev)
+        loss = (layer.getRenderBufferTF() * G).sum()
+        loss.backward()
+        if world > 1:
+            sharding.allreduce_shared_grads([d["sh_coeff"].grad, d["vertex_color"].grad])
+        for k in out_host:
+            out_host[k].copy_(d[k].grad, non_blocking=True)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e = {"value": round(world * V * args.steps / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": round(ms_e2e / args.steps, 4),
+           "resident": "texture and target_image (constants of a fit) stay in HBM; positions, colours, SH, cameras are copied every step"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        cpu_baseline = cpu_port_baseline(sc, seconds_budget=20.0)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "config2: UV-sphere 34970 verts / 69936 tris, 8 ring cameras, 1024x1024, ~52% coverage, vertexColor+shaded, "
+                                       "fwd+bwd (grads wrt positions, colours, SH), B=1 (8 views) per GPU per step",
+                           "views_per_step_per_gpu": V, "tile": args.tile or 32,
+                           "l2": "no explicit flush: a step streams ~300 MB of buffers (192 MB outputs + 100 MB render gradient) through a 126 MB L2",
+                           "collective": "none" if world == 1 else "1 NCCL all-reduce/step of shared SH + colour gradients (%d B)" % ((C * 27 + N * 3) * 4)},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_port_baseline(sc, seconds_budget=20.0, cameras=2):
+    """Oracle 2 (CPU port) on a bounded sample of the same workload: the first `cameras` cameras."""
+    from oracle import cpu
+    cpu.build()
+    N, W, H = sc["num_vertices"], sc["width"], sc["height"]
+    C = cameras
+    sl = lambda a, n: np.ascontiguousarray(a.reshape(1, sc["num_cameras"], n)[:, :C].reshape(1, C * n))
+    ex, it = sl(sc["extrinsics"], 12), sl(sc["intrinsics"], 9)
+    sh = np.ascontiguousarray(sc["sh_coeff"][:, :C])
+    rg = np.random.default_rng(3).standard_normal((1, C, H, W, 3)).astype(np.float32)
+    t0 = time.time()
+    reps = 0
+    while True:
+        o = cpu.forward(sc["faces"], sc["texcoords"], N, C, W, H, "vertexColor", "shaded", sc["vertex_pos"], sc["vertex_color"],
+                        sc["texture"], sh, ex, it)
+        cpu.backward(sc["faces"], sc["texcoords"], N, C, W, H, "vertexColor", "shaded", 1, rg, None, sc["vertex_pos"], sc["vertex_color"],
+                     sc["texture"], sh, sc["target_image"][:, :C], o["vertex_normal"], o["bary"], o["face"], ex, it)
+        reps += 1
+        dt = time.time() - t0
+        if dt > seconds_budget / 2 or reps >= 8:
+            break
+    return {"value": round(reps * C / dt, 3), "unit": UNIT, "cores": cpu.max_threads(), "kind": "port",
+            "sample": f"cameras 0..{C - 1} of the 8 at full size (70k tris, 1024x1024), fwd+bwd, {reps} repetition(s), {dt:.1f} s"}
+
+
+def run_reference(args, rank, world, local_rank):
+    """The reference arm: the UNMODIFIED reference renderer core (oracle/_ref/libgvv_ref.so, its CUDA
+    kernels compiled in place for sm_100a + the TF-free driver) on the same workload, one GPU.
+    The reference's implementation of this path is CUDA-only and single-GPU; when the library was
+    not shipped, the CPU port (Oracle 2) is timed instead."""
+    if rank != 0:
+        return
+    sc = make_inputs(0)
+    N, C, W, H = sc["num_vertices"], sc["num_cameras"], sc["width"], sc["height"]
+    from oracle import ref as oref
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config2 (same inputs as the ours arm), B=1 (8 views) per step"}}
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if oref.available() and have_gpu:
+        import torch
+        torch.cuda.set_device(local_rank)
+        dev = torch.device("cuda", local_rank)
+        ins = [torch.as_tensor(sc[k], device=dev) for k in INPUT_KEYS]
+        G = torch.randn((1, C, H, W, 3), generator=torch.Generator().manual_seed(3)).to(dev)
+        t0 = time.time()
+        ref = oref.RefRenderer(sc["faces"], sc["texcoords"], N, C, W, H, "vertexColor", "shaded")
+        ctor_s = time.time() - t0
+
+        def step():
+            o = ref.forward(*ins)
+            ref.backward(G, ins[0], ins[1], ins[2], ins[3], ins[4], o["vertex_normal"], o["bary"], o["face"], None, ins[5], ins[6])
+
+        for _ in range(max(1, min(args.warmup, 3))):
+            step()
+        steps = max(1, min(args.steps, 30))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        v = steps * C / (ms * 1e-3)
+        line.update(value=round(v, 3), steps=steps, ms_per_step=round(ms / steps, 3),
+                    cpu_baseline={"value": round(v, 3), "unit": UNIT, "cores": 1, "kind": "reference",
+                                  "sample": f"full workload, {steps} steps; the reference's own CUDA kernels on 1 GPU driven by 1 host thread "
+                                            f"(its path has no CPU implementation); constructor (O(N*F) host CSR, twice) {ctor_s:.1f} s excluded"},
+                    e2e={"value": round(v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    else:
+        cb = cpu_port_baseline(sc, seconds_budget=60.0)
+        cb["sample"] += " (oracle/_ref not available: CPU port timed instead)"
+        line.update(value=cb["value"], ms_per_step=round(1e3 * C / cb["value"], 2), cpu_baseline=cb,
+                    e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tile", type=int, default=0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world, local_rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

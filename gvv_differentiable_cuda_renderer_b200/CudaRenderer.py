@@ -16,6 +16,7 @@ import torch
 from . import _native
 
 _HANDLE_CACHE = OrderedDict()
+_IDENT_CACHE = {}
 _HANDLE_CACHE_MAX = 16
 
 
@@ -23,10 +24,15 @@ def _get_handle(faces, texcoords, N, C, U, V, albedo, shading, ifs, tfs, normal_
     """TF caches one OpKernel per attribute set; this is the same cache for gvv handles, so that
     building the layer every iteration of a fitting loop (as the reference's scripts do,
     python/test_gradients_VertexColor.py:104-121) does not rebuild topology or scratch."""
+    attrs = (int(N), int(C), int(U), int(V), albedo, shading, int(ifs), int(tfs), bool(normal_map), str(device))
+    # fast path: the very same attribute objects as last time (a fitting loop passes the same lists)
+    ident = (id(faces), id(texcoords)) + attrs
+    hit = _IDENT_CACHE.get(ident)
+    if hit is not None and hit[0] is faces and hit[1] is texcoords and hit[2]._h:
+        return hit[2]
     f = np.ascontiguousarray(np.asarray(faces, dtype=np.int32).reshape(-1))
     t = np.ascontiguousarray(np.asarray(texcoords, dtype=np.float32).reshape(-1))
-    key = (hashlib.sha1(f.tobytes()).hexdigest(), hashlib.sha1(t.tobytes()).hexdigest(), int(N), int(C), int(U), int(V),
-           albedo, shading, int(ifs), int(tfs), bool(normal_map), str(device))
+    key = (hashlib.sha1(f.tobytes()).hexdigest(), hashlib.sha1(t.tobytes()).hexdigest()) + attrs
     h = _HANDLE_CACHE.get(key)
     if h is None:
         h = _native.NativeRenderer(f, t, N, C, U, V, albedo, shading, ifs, tfs, normal_map, device)
@@ -35,10 +41,14 @@ def _get_handle(faces, texcoords, N, C, U, V, albedo, shading, ifs, tfs, normal_
             _HANDLE_CACHE.popitem(last=False)[1].close()
     else:
         _HANDLE_CACHE.move_to_end(key)
+    if len(_IDENT_CACHE) > 4 * _HANDLE_CACHE_MAX:
+        _IDENT_CACHE.clear()
+    _IDENT_CACHE[ident] = (faces, texcoords, h)   # strong refs keep the ids valid
     return h
 
 
 def clear_handle_cache():
+    _IDENT_CACHE.clear()
     while _HANDLE_CACHE:
         _HANDLE_CACHE.popitem()[1].close()
 

@@ -52,7 +52,8 @@ _lib = None
 
 # every symbol include/gvv_b200.h declares
 EXPORTS = ["gvv_create", "gvv_destroy", "gvv_forward", "gvv_backward", "gvv_last_error", "gvv_launch_count",
-           "gvv_debug_copy", "gvv_set_option", "gvv_bench_atomics"]
+           "gvv_debug_copy", "gvv_debug_eval", "gvv_set_option", "gvv_bench_atomics",
+           "gvv_kernel_count", "gvv_kernel_name", "gvv_kernel_times"]
 
 
 def lib():
@@ -76,8 +77,15 @@ def lib():
         L.gvv_launch_count.restype = i64
         L.gvv_debug_copy.argtypes = [vp, i32, vp, i64, vp]
         L.gvv_debug_copy.restype = i64
+        L.gvv_debug_eval.argtypes = [vp, i32, vp, vp, vp, vp]
+        L.gvv_debug_eval.restype = ctypes.c_int
         L.gvv_set_option.argtypes = [vp, ctypes.c_char_p, i32]
         L.gvv_set_option.restype = ctypes.c_int
+        L.gvv_kernel_count.restype = i32
+        L.gvv_kernel_name.argtypes = [i32]
+        L.gvv_kernel_name.restype = ctypes.c_char_p
+        L.gvv_kernel_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
+        L.gvv_kernel_times.restype = ctypes.c_int
         L.gvv_bench_atomics.argtypes = [i32, i32, i64, i64, i32, ctypes.POINTER(ctypes.c_double)]
         L.gvv_bench_atomics.restype = ctypes.c_int
         _lib = L
@@ -224,6 +232,30 @@ class NativeRenderer:
         if n < 0:
             raise GvvError("gvv_debug_copy failed")
         return buf[:min(n, nbytes)]
+
+
+def _eval_pairs(self, queries):
+    """queries int32 [n,4] = (view, x, y, face) -> (keys int32 [n], ab float32 [n,2]); key = INT32_MIN on a miss."""
+    q = np.ascontiguousarray(queries, dtype=np.int32).reshape(-1, 4)
+    keys = np.zeros(len(q), np.int32)
+    ab = np.zeros((len(q), 2), np.float32)
+    _check(lib().gvv_debug_eval(self._h, len(q), q.ctypes.data, keys.ctypes.data, ab.ctypes.data, self._stream()), "gvv_debug_eval")
+    return keys, ab
+
+
+NativeRenderer.eval_pairs = _eval_pairs
+
+
+def _kernel_times(self):
+    """{kernel name: (total device ms, launches)} since set_option('time_kernels', 1); clears the log."""
+    n = lib().gvv_kernel_count()
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_int64 * n)()
+    _check(lib().gvv_kernel_times(self._h, ms, cnt), "gvv_kernel_times")
+    return {lib().gvv_kernel_name(i).decode(): (ms[i], cnt[i]) for i in range(n) if cnt[i]}
+
+
+NativeRenderer.kernel_times = _kernel_times
 
 
 def bench_atomics(kind, n_addr, n_ops, iters=10, device=0):

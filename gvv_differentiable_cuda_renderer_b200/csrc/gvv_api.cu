@@ -163,6 +163,7 @@ extern "C" int gvv_destroy(gvv_handle h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   free_scratch(h->s);
+  if (h->timer.ev) { for (int i = 0; i < 2 * KernelTimer::kCap; ++i) cudaEventDestroy(h->timer.ev[i]); delete[] h->timer.ev; delete[] h->timer.slot; }
   cudaFree(h->faces4); cudaFree(h->texcoords); cudaFree(h->vfOffsets); cudaFree(h->vfList); cudaFree(h->texelTable);
   delete h;
   return GVV_OK;
@@ -178,6 +179,20 @@ extern "C" int gvv_set_option(gvv_handle h, const char* key, int32_t value) {
       free_scratch(h->s);
       set_tile(h, value);
     }
+    return GVV_OK;
+  }
+  if (!strcmp(key, "time_kernels")) {
+    KernelTimer& t = h->timer;
+    cudaSetDevice(h->device);
+    if (value && !t.ev) {
+      t.ev = new (std::nothrow) cudaEvent_t[2 * KernelTimer::kCap];
+      t.slot = new (std::nothrow) int[KernelTimer::kCap];
+      if (!t.ev || !t.slot) return fail(GVV_ENOMEM, "out of host memory");
+      for (int i = 0; i < 2 * KernelTimer::kCap; ++i)
+        if (cudaEventCreate(&t.ev[i]) != cudaSuccess) return fail(GVV_ECUDA, "cudaEventCreate failed");
+    }
+    t.used = 0;
+    t.enabled = value != 0;
     return GVV_OK;
   }
   return fail(GVV_EINVAL, "unknown option '%s'", key);
@@ -234,7 +249,7 @@ extern "C" int gvv_forward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
     }
     n = launch_normal_map(a, h->texelTable, normal_map, st);
   } else {
-    n = launch_forward(a, st);
+    n = launch_forward(a, st, &h->timer);
   }
   if (n < 0) return fail(GVV_ECUDA, "forward launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   h->launches += n;
@@ -275,7 +290,7 @@ extern "C" int gvv_backward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
   a.face = face; a.faces4 = h->faces4; a.vfOffsets = h->vfOffsets; a.vfList = h->vfList;
   a.vpos_grad = vpos_grad; a.vcol_grad = vcol_grad; a.tex_grad = tex_grad; a.sh_grad = sh_grad;
   a.s = h->s;
-  const int n = launch_backward(a, st);
+  const int n = launch_backward(a, st, &h->timer);
   if (n < 0) return fail(GVV_ECUDA, "backward launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   h->launches += n;
   return GVV_OK;
@@ -295,4 +310,52 @@ extern "C" int64_t gvv_debug_copy(gvv_handle h, int32_t which, void* dst, int64_
   if (cudaMemcpyAsync(dst, src, (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
   if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
   return bytes;
+}
+
+extern "C" int gvv_debug_eval(gvv_handle h, int32_t n, const int32_t* queries, int32_t* out_key, float* out_ab, void* stream) {
+  if (!h || n < 0 || (n > 0 && (!queries || !out_key || !out_ab))) return fail(GVV_EINVAL, "gvv_debug_eval: bad argument");
+  if (n == 0) return GVV_OK;
+  if (!h->s.cams) return fail(GVV_EINVAL, "gvv_debug_eval: no forward call yet");
+  for (int i = 0; i < n; ++i) {
+    const int32_t* q = queries + 4 * i;
+    if (q[0] < 0 || q[0] >= h->s.capViews || q[1] < 0 || q[1] >= h->W || q[2] < 0 || q[2] >= h->H || q[3] < 0 || q[3] >= h->F)
+      return fail(GVV_EINVAL, "gvv_debug_eval: query %d out of range", i);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  int *dq = nullptr, *dk = nullptr; float* da = nullptr;
+  CK(cudaMalloc((void**)&dq, sizeof(int) * 4 * (size_t)n));
+  CK(cudaMalloc((void**)&dk, sizeof(int) * (size_t)n));
+  CK(cudaMalloc((void**)&da, sizeof(float) * 2 * (size_t)n));
+  CK(cudaMemcpyAsync(dq, queries, sizeof(int) * 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+  const int k = launch_debug_eval(h->s, h->faces4, h->N, h->C, h->W, h->H, n, dq, dk, da, st);
+  if (k > 0) h->launches += k;
+  CK(cudaMemcpyAsync(out_key, dk, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out_ab, da, sizeof(float) * 2 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(dq); cudaFree(dk); cudaFree(da);
+  return k > 0 ? GVV_OK : fail(GVV_ECUDA, "debug_eval launch failed");
+}
+
+static const char* kKernelNames[K_NUM_SLOTS] = {"camera_kernel", "vertex_kernel", "bin_count_kernel", "bin_scan_kernel",
+                                                "bin_fill_kernel", "raster_kernel", "zero_kernel", "pixel_grad_kernel",
+                                                "normal_term_kernel", "normal_map_kernel"};
+
+extern "C" int32_t gvv_kernel_count(void) { return K_NUM_SLOTS; }
+extern "C" const char* gvv_kernel_name(int32_t i) { return (i >= 0 && i < K_NUM_SLOTS) ? kKernelNames[i] : ""; }
+
+extern "C" int gvv_kernel_times(gvv_handle h, double* total_ms, int64_t* launches) {
+  if (!h || !total_ms || !launches) return fail(GVV_EINVAL, "gvv_kernel_times: null argument");
+  for (int i = 0; i < K_NUM_SLOTS; ++i) { total_ms[i] = 0.0; launches[i] = 0; }
+  KernelTimer& t = h->timer;
+  CK(cudaSetDevice(h->device));
+  for (int r = 0; r < t.used; ++r) {
+    CK(cudaEventSynchronize(t.ev[2 * r + 1]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, t.ev[2 * r], t.ev[2 * r + 1]));
+    total_ms[t.slot[r]] += ms;
+    launches[t.slot[r]] += 1;
+  }
+  t.used = 0;
+  return GVV_OK;
 }

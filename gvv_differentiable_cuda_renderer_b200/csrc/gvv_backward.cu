@@ -355,9 +355,11 @@ normal_term_kernel(const float* __restrict__ vertex_pos, const float* __restrict
 // ------------------------------------------------------------------------------------------------
 int launch_camera(const float* extr, const float* intr, CamRec* cams, int* bigCount, int V, cudaStream_t st);
 
-int launch_backward(const BwdArgs& a, cudaStream_t st) {
+int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const int V = a.B * a.C;
+  tm->begin(K_CAMERA, st);
   int launches = launch_camera(a.extrinsics, a.intrinsics, a.s.cams, nullptr, V, st);
+  tm->end(st);
   ZeroArgs z;
   const long long nv = (long long)a.B * a.N * 3;
   z.p[0] = a.vpos_grad; z.n[0] = nv;
@@ -365,7 +367,9 @@ int launch_backward(const BwdArgs& a, cudaStream_t st) {
   z.p[2] = a.s.gnorm;   z.n[2] = nv;
   z.p[3] = a.sh_grad;   z.n[3] = (long long)V * 27;
   z.p[4] = a.tex_grad;  z.n[4] = a.tex_grad ? (long long)a.B * a.texH * a.texW * 3 : 0;
+  tm->begin(K_ZERO, st);
   zero_kernel<<<148 * 8, 256, 0, st>>>(z);
+  tm->end(st);
   ++launches;
   PixelParams p;
   p.render_grad = a.render_grad; p.target_grad = a.target_grad; p.vertex_pos = a.vertex_pos; p.vertex_color = a.vertex_color;
@@ -374,11 +378,15 @@ int launch_backward(const BwdArgs& a, cudaStream_t st) {
   p.vpos_grad = a.vpos_grad; p.vcol_grad = a.vcol_grad; p.tex_grad = a.tex_grad; p.sh_grad = a.sh_grad; p.gnorm = a.s.gnorm;
   p.C = a.C; p.N = a.N; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
   p.albedo = a.albedo; p.shading = a.shading; p.imgFilter = a.imgFilter;
+  tm->begin(K_PIXEL_GRAD, st);
   pixel_grad_kernel<<<dim3((a.W + 31) / 32, (a.H + 7) / 8, V), 256, 0, st>>>(p);
+  tm->end(st);
   ++launches;
   if (a.shading == GVV_SHADING_SHADED) {
+    tm->begin(K_NORMAL_TERM, st);
     normal_term_kernel<<<dim3((a.N + 127) / 128, a.B), 128, 0, st>>>(a.vertex_pos, a.s.gnorm, a.faces4, a.vfOffsets, a.vfList,
                                                                     a.vpos_grad, a.N);
+    tm->end(st);
     ++launches;
   }
   return cudaGetLastError() == cudaSuccess ? launches : -1;

@@ -475,6 +475,35 @@ raster_kernel(const RasterParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// debug: one exact (pixel, triangle) evaluation per thread (same device functions as the raster)
+// ------------------------------------------------------------------------------------------------
+__global__ void debug_eval_kernel(const CamRec* __restrict__ cams, const float4* __restrict__ vscaled, const float4* __restrict__ proj,
+                                  const int4* __restrict__ faces4, int N, int C, int n, const int* __restrict__ q,
+                                  int* __restrict__ key, float* __restrict__ ab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int view = q[4 * i], x = q[4 * i + 1], y = q[4 * i + 2], f = q[4 * i + 3];
+  const CamRec* cam = cams + view;
+  const int b = view / C;
+  const int4 fc = faces4[f];
+  const float4 s0 = vscaled[(size_t)b * N + fc.x], s1 = vscaled[(size_t)b * N + fc.y], s2 = vscaled[(size_t)b * N + fc.z];
+  const float4 p0 = proj[(size_t)view * N + fc.x], p1 = proj[(size_t)view * N + fc.y], p2 = proj[(size_t)view * N + fc.z];
+  const F3 ros = mk3(cam->ros[0], cam->ros[1], cam->ros[2]);
+  const TriSetup ts = tri_setup_exact(mk3(s0.x, s0.y, s0.z), mk3(s1.x, s1.y, s1.z), mk3(s2.x, s2.y, s2.z), ros);
+  const F3 rd = ray_dir_exact(cam->Pinv, cam->ro, __fadd_rn((float)x, 0.5f), __fadd_rn((float)y, 0.5f));
+  float a = 0.f, bq = 0.f, c = 0.f;
+  const bool hit = hit_exact(ts, ros, rd, a, bq, c);
+  key[i] = hit ? depth_key_exact(a, bq, c, p0.z, p1.z, p2.z) : (int)0x80000000;
+  ab[2 * i] = hit ? a : -1.f; ab[2 * i + 1] = hit ? bq : -1.f;
+}
+
+int launch_debug_eval(const Scratch& s, const int4* faces4, int N, int C, int W, int H, int n, const int* dq, int* dkey, float* dab, cudaStream_t st) {
+  (void)W; (void)H;
+  debug_eval_kernel<<<(n + 127) / 128, 128, 0, st>>>(s.cams, s.vscaled, s.proj, faces4, N, C, n, dq, dkey, dab);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // launcher
 // ------------------------------------------------------------------------------------------------
 static inline bool launch_ok() { return cudaGetLastError() == cudaSuccess; }
@@ -484,15 +513,20 @@ int launch_camera(const float* extr, const float* intr, CamRec* cams, int* bigCo
   return 1;
 }
 
-int launch_forward(const FwdArgs& a, cudaStream_t st) {
+int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const int V = a.B * a.C;
+  tm->begin(K_CAMERA, st);
   int launches = launch_camera(a.extrinsics, a.intrinsics, a.s.cams, a.s.bigCount, V, st);
+  tm->end(st);
+  tm->begin(K_VERTEX, st);
   vertex_kernel<<<dim3((a.N + 127) / 128, a.B), 128, 0, st>>>(a.vertex_pos, a.vertex_color, a.faces4, a.vfOffsets, a.vfList,
                                                              a.s.cams, a.s.proj, a.s.vscaled, a.s.vnorm4, a.s.vcol4,
                                                              a.vertex_normal, a.N, a.C);
+  tm->end(st);
   ++launches;
   const int tileShift = a.tile == 32 ? 5 : 4;
   const dim3 gridF((a.F + 255) / 256, V);
+  tm->begin(K_BIN_COUNT, st);
   if (a.nT <= kSmemHistTiles) {
     bin_count_kernel<true><<<gridF, 256, a.nT * sizeof(int), st>>>(a.faces4, a.s.proj, a.s.tileCount, a.s.bigCount, a.s.bigList,
                                                                   a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
@@ -500,9 +534,13 @@ int launch_forward(const FwdArgs& a, cudaStream_t st) {
     bin_count_kernel<false><<<gridF, 256, 0, st>>>(a.faces4, a.s.proj, a.s.tileCount, a.s.bigCount, a.s.bigList,
                                                   a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
   }
+  tm->end(st);
   ++launches;
+  tm->begin(K_BIN_SCAN, st);
   bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.nT);
+  tm->end(st);
   ++launches;
+  tm->begin(K_BIN_FILL, st);
   if (a.nT <= kSmemHistTiles) {
     bin_fill_kernel<true><<<gridF, 256, 2 * a.nT * sizeof(int), st>>>(a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCursor, a.s.bins,
                                                                      a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
@@ -510,6 +548,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st) {
     bin_fill_kernel<false><<<gridF, 256, 0, st>>>(a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCursor, a.s.bins,
                                                  a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
   }
+  tm->end(st);
   ++launches;
   RasterParams p;
   p.faces4 = a.faces4; p.proj = a.s.proj; p.vscaled = a.s.vscaled; p.vnorm4 = a.s.vnorm4; p.vcol4 = a.s.vcol4;
@@ -520,8 +559,10 @@ int launch_forward(const FwdArgs& a, cudaStream_t st) {
   p.C = a.C; p.N = a.N; p.F = a.F; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
   p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT;
   const dim3 gridT(a.nT, V);
+  tm->begin(K_RASTER, st);
   if (a.tile == 16) raster_kernel<16><<<gridT, 256, 0, st>>>(p);
   else raster_kernel<32><<<gridT, 256, 0, st>>>(p);
+  tm->end(st);
   ++launches;
   return launch_ok() ? launches : -1;
 }

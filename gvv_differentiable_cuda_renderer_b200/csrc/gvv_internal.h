@@ -29,6 +29,23 @@ struct Scratch {
   float* gnorm = nullptr;        // [B*N*3] backward: dL/d(unnormalised vertex normal)
 };
 
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py roofline leg).
+enum KernelSlot { K_CAMERA = 0, K_VERTEX, K_BIN_COUNT, K_BIN_SCAN, K_BIN_FILL, K_RASTER, K_ZERO, K_PIXEL_GRAD, K_NORMAL_TERM, K_NORMAL_MAP, K_NUM_SLOTS };
+
+struct KernelTimer {
+  bool enabled = false;
+  static constexpr int kCap = 4096;
+  cudaEvent_t* ev = nullptr;   // 2*kCap events, created on first enable
+  int* slot = nullptr;
+  int used = 0;
+  inline void begin(int s, cudaStream_t st) {
+    if (enabled && used < kCap) { slot[used] = s; cudaEventRecord(ev[2 * used], st); }
+  }
+  inline void end(cudaStream_t st) {
+    if (enabled && used < kCap) { cudaEventRecord(ev[2 * used + 1], st); ++used; }
+  }
+};
+
 }  // namespace gvv
 
 struct gvv_renderer {
@@ -45,6 +62,7 @@ struct gvv_renderer {
   float4* texelTable = nullptr; int tableH = 0, tableW = 0;
   gvv::Scratch s;
   int64_t launches = 0;
+  gvv::KernelTimer timer;
 };
 
 namespace gvv {
@@ -72,9 +90,10 @@ struct BwdArgs {
 };
 
 // Each returns the number of kernels launched, or -1 after a launch error.
-int launch_forward(const FwdArgs& a, cudaStream_t st);
+int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm);
 int launch_normal_map(const FwdArgs& a, const float4* texelTable, float* normal_map, cudaStream_t st);
-int launch_backward(const BwdArgs& a, cudaStream_t st);
+int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm);
+int launch_debug_eval(const Scratch& s, const int4* faces4, int N, int C, int W, int H, int n, const int* dq, int* dkey, float* dab, cudaStream_t st);
 int launch_build_texel_table(const float* texcoords, int F, int texH, int texW, float4* table, cudaStream_t st);
 
 }  // namespace gvv

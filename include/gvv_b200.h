@@ -128,8 +128,22 @@ int64_t gvv_launch_count(gvv_handle h);
  * Returns the number of bytes the buffer holds (copies min(bytes, capacity)). */
 int64_t gvv_debug_copy(gvv_handle h, int32_t which, void* host_dst, int64_t capacity, void* stream);
 
-/* Runtime knobs: key "tile" (16|32 rasteriser tile edge; default 32). Returns 0 on success. */
+/* Re-evaluates the exact (pixel, triangle) test on the geometry of the LAST forward call, for
+ * tie analysis in the parity tests.  queries: HOST int32[n*4] = (view, x, y, face);
+ * out_key: HOST int32[n] depth key as the reference's atomicMin sees it, INT32_MIN when the pair
+ * fails the inside test; out_ab: HOST float[n*2] barycentrics (a,b).  Synchronises `stream`. */
+int gvv_debug_eval(gvv_handle h, int32_t n, const int32_t* queries, int32_t* out_key, float* out_ab, void* stream);
+
+/* Runtime knobs: key "tile" (16|32 rasteriser tile edge; default 32); key "time_kernels" (1: record
+ * a CUDA-event pair around every kernel on the launching stream, 0: off; either resets the log).
+ * Returns 0 on success. */
 int gvv_set_option(gvv_handle h, const char* key, int32_t value);
+
+/* Per-kernel device time accumulated since "time_kernels" was enabled (synchronises): total_ms and
+ * launches are arrays of gvv_kernel_count() entries, named by gvv_kernel_name(i).  Clears the log. */
+int32_t gvv_kernel_count(void);
+const char* gvv_kernel_name(int32_t i);
+int gvv_kernel_times(gvv_handle h, double* total_ms, int64_t* launches);
 
 /* Atomic-throughput micro-benchmark used for the roofline denominators:
  * kind 0: red.global.min.u64 over `n_addr` 64-bit words, kind 1: red.global.add.f32 over

@@ -1,0 +1,116 @@
+"""GPU (-m gpu): the drop-in Python layer (CudaRendererGpu) -- headless restatements of the
+reference's four scripts (python/test_render.py, python/test_gradients_*.py): same call pattern,
+assertions instead of cv.imshow."""
+import numpy as np
+import pytest
+import torch
+
+from gvv_differentiable_cuda_renderer_b200 import CudaRendererGpu, synthetic
+from gvv_differentiable_cuda_renderer_b200.CudaRenderer import _HANDLE_CACHE
+
+pytestmark = pytest.mark.gpu
+
+
+def scene(**kw):
+    sc = synthetic.make_scene(**kw)
+    dev = torch.device("cuda:0")
+    t = {k: torch.as_tensor(v, device=dev) for k, v in sc.items() if isinstance(v, np.ndarray) and v.dtype == np.float32 and k != "texcoords"}
+    return sc, t
+
+
+def layer(sc, t, albedo, shading, **over):
+    a = dict(vertexPos_input=t["vertex_pos"], vertexColor_input=t["vertex_color"], texture_input=t["texture"],
+             shCoeff_input=t["sh_coeff"], targetImage_input=t["target_image"], extrinsics_input=t["extrinsics"],
+             intrinsics_input=t["intrinsics"])
+    a.update(over)
+    return CudaRendererGpu(faces_attr=sc["faces"].reshape(-1).tolist(), texCoords_attr=sc["texcoords"].reshape(-1).tolist(),
+                           numberOfVertices_attr=sc["num_vertices"], numberOfCameras_attr=sc["num_cameras"],
+                           renderResolutionU_attr=sc["width"], renderResolutionV_attr=sc["height"],
+                           albedoMode_attr=albedo, shadingMode_attr=shading, **a)
+
+
+def test_render_script_restated():
+    """python/test_render.py: B=2, vertexColor + shaded, forward only."""
+    sc, t = scene(kind="pyramid", cameras=1, width=128, height=128, batch=2)
+    r = layer(sc, t, "vertexColor", "shaded")
+    img = r.getRenderBufferTF()
+    assert img.shape == (2, 1, 128, 128, 3) and r.getFaceBufferTF().dtype == torch.int32
+    mask = r.getModelMaskTF()
+    assert mask.shape == img.shape and 0.02 < float(mask.mean()) < 0.9
+    assert r.getRenderBufferOpenCV(0, 0).shape == (128, 128, 3)
+    assert torch.equal(r.getTargetBufferTF(), t["target_image"])
+    assert r.getNormalMap() is None
+
+
+def test_sh_fitting_restated():
+    """python/test_gradients_SphericalHarmonics.py: Adam(lr 0.01) on l2 loss, shared SH [1,1,27]."""
+    sc, t = scene(kind="sphere", rings=16, segments=20, cameras=2, width=96, height=96, batch=3)
+    base = torch.as_tensor(synthetic.base_sh(), device="cuda:0").reshape(1, 1, 27)
+    target = layer(sc, t, "vertexColor", "shaded", shCoeff_input=base.expand(3, 2, 27).contiguous()).getRenderBufferTF().detach()
+    sh = (base + 0.5 * torch.rand(1, 1, 27, device="cuda:0", generator=torch.Generator("cuda").manual_seed(0))).requires_grad_(True)
+    opt = torch.optim.Adam([sh], lr=0.01)
+    losses = []
+    n0 = len(_HANDLE_CACHE)
+    for _ in range(30):
+        opt.zero_grad()
+        out = layer(sc, t, "vertexColor", "shaded", shCoeff_input=sh.expand(3, 2, 27)).getRenderBufferTF()
+        loss = 0.5 * ((out - target) ** 2).sum()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < 0.6 * losses[0], losses
+    assert len(_HANDLE_CACHE) <= n0 + 1          # the handle is cached across iterations, like a TF kernel
+
+
+def test_vertex_colour_fitting_restated():
+    """python/test_gradients_VertexColor.py: SGD on sum((out-target)^2)/(C*N) from zero colours."""
+    sc, t = scene(kind="sphere", rings=16, segments=20, cameras=2, width=96, height=96)
+    target = layer(sc, t, "vertexColor", "shaded").getRenderBufferTF().detach()
+    col = torch.zeros_like(t["vertex_color"]).requires_grad_(True)
+    opt = torch.optim.SGD([col], lr=10.0)
+    losses = []
+    for _ in range(10):
+        opt.zero_grad()
+        out = layer(sc, t, "vertexColor", "shaded", vertexColor_input=col).getRenderBufferTF()
+        loss = ((out - target) ** 2).sum() / (sc["num_cameras"] * sc["num_vertices"])
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < 0.7 * losses[0], losses
+
+
+def test_texture_fitting_restated():
+    """python/test_gradients_Texture.py: textured + shadeless, the target render passed as targetImage."""
+    sc, t = scene(kind="sphere", rings=16, segments=20, cameras=1, width=96, height=96, tex=32)
+    target = layer(sc, t, "textured", "shadeless").getRenderBufferTF().detach()
+    tex = torch.ones_like(t["texture"]).requires_grad_(True)
+    opt = torch.optim.SGD([tex], lr=0.05)
+    losses = []
+    for _ in range(40):
+        opt.zero_grad()
+        r = layer(sc, t, "textured", "shadeless", texture_input=tex, targetImage_input=target)
+        loss = ((r.getRenderBufferTF() - r.getTargetBufferTF()) ** 2).sum()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < 0.5 * losses[0], losses
+
+
+def test_gradient_rules_of_the_python_layer():
+    sc, t = scene(kind="sphere", rings=10, segments=12, cameras=1, width=48, height=48)
+    leaves = {k: t[k].clone().requires_grad_(True) for k in ("vertex_pos", "vertex_color", "texture", "sh_coeff", "target_image", "extrinsics", "intrinsics")}
+    kw = dict(vertexPos_input=leaves["vertex_pos"], vertexColor_input=leaves["vertex_color"], texture_input=leaves["texture"],
+              shCoeff_input=leaves["sh_coeff"], targetImage_input=leaves["target_image"], extrinsics_input=leaves["extrinsics"],
+              intrinsics_input=leaves["intrinsics"])
+    # normal / lighting albedo: all-zero gradients (CudaRenderer.py:207-213)
+    layer(sc, t, "normal", "shaded", **kw).getRenderBufferTF().sum().backward()
+    assert all(float(v.grad.abs().max()) == 0 for v in leaves.values())
+    for v in leaves.values():
+        v.grad = None
+    # vertexColor: position/colour/SH get gradients, target/extrinsics/intrinsics zeros (CudaRenderer.py:215)
+    r = layer(sc, t, "vertexColor", "shaded", **kw)
+    (r.getRenderBufferTF().sum() + r.getTargetBufferTF().sum()).backward()
+    assert float(leaves["vertex_color"].grad.abs().max()) > 0 and float(leaves["sh_coeff"].grad.abs().max()) > 0
+    assert float(leaves["vertex_pos"].grad.abs().max()) > 0
+    for k in ("target_image", "extrinsics", "intrinsics"):
+        assert float(leaves[k].grad.abs().max()) == 0
