@@ -40,7 +40,7 @@ static cudaError_t dmalloc(T** p, size_t count) {
 static void free_scratch(Scratch& s) {
   cudaFree(s.cams); cudaFree(s.proj); cudaFree(s.vscaled); cudaFree(s.vnorm4); cudaFree(s.vcol4);
   cudaFree(s.tileCount); cudaFree(s.tileCursor); cudaFree(s.tileOffset); cudaFree(s.bigCount);
-  cudaFree(s.bigList); cudaFree(s.bins); cudaFree(s.gnorm);
+  cudaFree(s.bigList); cudaFree(s.bins); cudaFree(s.gnorm); cudaFree(s.bpos4); cudaFree(s.bcol4); cudaFree(s.bnor4);
   s = Scratch();
 }
 
@@ -73,6 +73,9 @@ static int ensure_scratch(gvv_renderer* h, int B, cudaStream_t st) {
   acc(dmalloc(&s.bigList, (size_t)V * F));
   acc(dmalloc(&s.bins, (size_t)V * F * kMaxSmallTiles));
   acc(dmalloc(&s.gnorm, (size_t)B * N * 3));
+  acc(dmalloc(&s.bpos4, (size_t)B * N));
+  acc(dmalloc(&s.bcol4, (size_t)B * N));
+  acc(dmalloc(&s.bnor4, (size_t)V * N));
   if (e != cudaSuccess) {
     free_scratch(s);
     return fail(GVV_ENOMEM, "scratch allocation for %d views failed: %s", V, cudaGetErrorString(e));
@@ -181,6 +184,10 @@ extern "C" int gvv_set_option(gvv_handle h, const char* key, int32_t value) {
     }
     return GVV_OK;
   }
+  if (!strcmp(key, "cull_margin_milli")) {   // fixed part of the pre-test margin in 1/1000 px; < 0 = no culling
+    h->cullMargin = value < 0 ? -1.f : (float)value / 1000.f;
+    return GVV_OK;
+  }
   if (!strcmp(key, "time_kernels")) {
     KernelTimer& t = h->timer;
     cudaSetDevice(h->device);
@@ -221,7 +228,7 @@ extern "C" int gvv_forward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
   FwdArgs a;
   a.B = B; a.C = h->C; a.N = h->N; a.F = h->F; a.W = h->W; a.H = h->H; a.texH = texH; a.texW = texW;
   a.albedo = h->albedo; a.shading = h->shading;
-  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT;
+  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin;
   a.vertex_pos = vertex_pos; a.vertex_color = vertex_color; a.texture = texture; a.sh_coeff = sh_coeff;
   a.extrinsics = extrinsics; a.intrinsics = intrinsics; a.texcoords = h->texcoords;
   a.faces4 = h->faces4; a.vfOffsets = h->vfOffsets; a.vfList = h->vfList;

@@ -96,13 +96,51 @@ struct PixelParams {
   const int32_t* face;
   const int4* faces4;
   const CamRec* cams;
+  const float4 *pos4, *col4, *nor4;
   float *vpos_grad, *vcol_grad, *tex_grad, *sh_grad, *gnorm;
   int C, N, W, H, texH, texW, albedo, shading, imgFilter;
 };
 
 constexpr int kVals = 27;
 
-__global__ void __launch_bounds__(256)
+// Tolerance-level arithmetic of the backward: reciprocal-multiply instead of IEEE divides
+// (gradients are compared to rel-L2 1e-4; the visibility-critical ray uses the exact functions).
+__device__ __forceinline__ float rcpf(float x) { return __frcp_rn(x); }
+
+__device__ __forceinline__ void bary_vjp_fast(V3 o, V3 d, V3 v0, V3 v1, V3 v2, float alpha, float beta, V3& g0, V3& g1, V3& g2) {
+  g0 = g1 = g2 = v3(0.f, 0.f, 0.f);
+  const V3 e01 = v1 - v0, e02 = v2 - v0;
+  const V3 N = cross(e01, e02);
+  const float D = dot(N, N);
+  const float nd = dot(d, N);
+  // |dot(normalize(d), normalize(N))| < 0.001  <=>  nd^2 < 1e-6 * |d|^2 * D   (RendererUtil.h:682)
+  if (nd * nd < 1.0e-6f * dot(d, d) * D || fabsf(D * D) < 0.001f) return;
+  const float iD = rcpf(D), ind = rcpf(nd);
+  const V3 w = v0 - o;
+  const float t = dot(w, N) * ind;
+  const V3 P = o + t * d;
+  const V3 E1 = v2 - v1, p1 = P - v1, C1 = cross(E1, p1);
+  const V3 E2 = v0 - v2, p2 = P - v2, C2 = cross(E2, p2);
+  const float A = dot(N, C1), Bn = dot(N, C2);
+  const float Ab = alpha * iD, Bb = beta * iD;
+  const float Db = -(alpha * A + beta * Bn) * iD * iD;
+  V3 Nb = Ab * C1 + Bb * C2 + (2.f * Db) * N;
+  const V3 C1b = Ab * N, C2b = Bb * N;
+  const V3 E1b = cross(p1, C1b), p1b = cross(C1b, E1);
+  const V3 E2b = cross(p2, C2b), p2b = cross(C2b, E2);
+  const float tb = dot(p1b + p2b, d);
+  const float mb = tb * ind;
+  Nb = Nb + mb * w + (-mb * t) * d;
+  const V3 e01b = cross(e02, Nb), e02b = cross(Nb, e01);
+  g0 = E2b + mb * N - e01b - e02b;
+  g1 = e01b - p1b - E1b;
+  g2 = e02b - p2b + E1b - E2b;
+}
+
+__device__ __forceinline__ V3 ld4(const float4* __restrict__ p, size_t i) { const float4 v = __ldg(p + i); return v3(v.x, v.y, v.z); }
+
+// grid (W/32, H/8, V), 256 threads: warp w owns the 32-pixel scanline segment y = 8*by + w.
+__global__ void __launch_bounds__(256, 3)
 pixel_grad_kernel(const PixelParams p) {
   __shared__ float buf[8][32 * kVals];
   __shared__ float shPart[8][kVals];
@@ -124,15 +162,14 @@ pixel_grad_kernel(const PixelParams p) {
   __syncthreads();
 
   float* mybuf = buf[warp];
+  float* mine = mybuf + lane * kVals;
   const unsigned cv = __ballot_sync(FULL_MASK, covered);
-  float shv[kVals];
+  float gA[3] = {0.f, 0.f, 0.f};
+  float Y[9];
 #pragma unroll
-  for (int j = 0; j < kVals; ++j) shv[j] = 0.f;
+  for (int k = 0; k < 9; ++k) Y[k] = 0.f;
 
   if (cv) {
-    float val[kVals];
-#pragma unroll
-    for (int j = 0; j < kVals; ++j) val[j] = 0.f;
     if (covered) {
       // ---- per-pixel setup (CUDABasedRasterizationGrad.cu:205-240) ----
       const F3 rdx = ray_dir_exact(cam.Pinv, cam.ro, (float)x + 0.5f, (float)y + 0.5f);
@@ -140,18 +177,20 @@ pixel_grad_kernel(const PixelParams p) {
       const float2 ab = __ldg(reinterpret_cast<const float2*>(p.bary) + pix);
       const float bc[3] = {ab.x, ab.y, 1.f - ab.x - ab.y};
       const int4 fc = __ldg(p.faces4 + face);
-      const float* pos = p.vertex_pos + (size_t)b * p.N * 3;
-      const float* nor = p.vertex_normal + (size_t)view * p.N * 3;
-      const V3 p0 = ldv3(pos, fc.x), p1 = ldv3(pos, fc.y), p2 = ldv3(pos, fc.z);
-      const V3 n0 = ldv3(nor, fc.x), n1 = ldv3(nor, fc.y), n2 = ldv3(nor, fc.z);
+      const float4* pos = p.pos4 + (size_t)b * p.N;
+      const float4* nor = p.nor4 + (size_t)view * p.N;
+      const V3 p0 = ld4(pos, fc.x), p1 = ld4(pos, fc.y), p2 = ld4(pos, fc.z);
+      const V3 n0 = ld4(nor, fc.x), n1 = ld4(nor, fc.y), n2 = ld4(nor, fc.z);
       const V3 nUn = bc[0] * n0 + bc[1] * n1 + bc[2] * n2;
-      const float len = sqrtf(dot(nUn, nUn));
-      V3 n = v3(nUn.x / len, nUn.y / len, nUn.z / len);
+      const float len2 = dot(nUn, nUn);
+      const float ilen = rsqrtf(len2);
+      V3 n = ilen * nUn;
       const bool flipped = dot(n, d) > 0.f;
       if (flipped) n = v3(-n.x, -n.y, -n.z);
 
       // SH basis (getIllum / getJLiGm, RendererUtil.h:179-214,351-364)
-      const float Y[9] = {1.f, n.y, n.z, n.x, n.x * n.y, n.z * n.y, 3.f * n.z * n.z - 1.f, n.x * n.z, n.x * n.x - n.y * n.y};
+      Y[0] = 1.f; Y[1] = n.y; Y[2] = n.z; Y[3] = n.x; Y[4] = n.x * n.y; Y[5] = n.z * n.y;
+      Y[6] = 3.f * n.z * n.z - 1.f; Y[7] = n.x * n.z; Y[8] = n.x * n.x - n.y * n.y;
       float light[3];
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
@@ -166,14 +205,14 @@ pixel_grad_kernel(const PixelParams p) {
       // ---- albedo (:242-319) and its gradients (:327-395) ----
       float alb[3] = {0.f, 0.f, 0.f};
       if (p.albedo == GVV_ALBEDO_VERTEX_COLOR) {
-        const float* col = p.vertex_color + (size_t)b * p.N * 3;
-        const V3 c0 = ldv3(col, fc.x), c1 = ldv3(col, fc.y), c2 = ldv3(col, fc.z);
+        const float4* col = p.col4 + (size_t)b * p.N;
+        const V3 c0 = ld4(col, fc.x), c1 = ld4(col, fc.y), c2 = ld4(col, fc.z);
         const V3 al = bc[0] * c0 + bc[1] * c1 + bc[2] * c2;
         alb[0] = al.x; alb[1] = al.y; alb[2] = al.z;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int ch = 0; ch < 3; ++ch) val[i * 3 + ch] = gl[ch] * bc[i];
+          for (int ch = 0; ch < 3; ++ch) mine[i * 3 + ch] = gl[ch] * bc[i];
       } else if (p.albedo == GVV_ALBEDO_TEXTURED) {
         const float* tc = p.texcoords + (size_t)face * 6;
         float u = (__ldg(tc + 0) * bc[0] + __ldg(tc + 2) * bc[1] + __ldg(tc + 4) * bc[2]) * p.texW;
@@ -196,14 +235,12 @@ pixel_grad_kernel(const PixelParams p) {
           atomicAdd(tg + 0, gl[0]); atomicAdd(tg + 1, gl[1]); atomicAdd(tg + 2, gl[2]);
         }
       }
-      const float gA[3] = {g.x * alb[0], g.y * alb[1], g.z * alb[2]};
+      gA[0] = g.x * alb[0]; gA[1] = g.y * alb[1]; gA[2] = g.z * alb[2];
 
+      float pos9[9];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) pos9[j] = 0.f;
       if (shaded) {
-        // ---- SH gradient (:402-436) ----
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch)
-#pragma unroll
-          for (int k = 0; k < 9; ++k) shv[ch * 9 + k] = gA[ch] * Y[k];
         // ---- position gradient through the shading normal (:458-525) ----
         V3 u3 = v3(0.f, 0.f, 0.f);   // (g*albedo) * JLiNo  (RendererUtil.h:371-391)
 #pragma unroll
@@ -213,19 +250,20 @@ pixel_grad_kernel(const PixelParams p) {
           u3.y += gA[ch] * (s[1] + s[4] * n.x + s[5] * n.z + s[8] * -2.f * n.y);
           u3.z += gA[ch] * (s[2] + s[5] * n.y + s[6] * 6.f * n.z + s[7] * n.x);
         }
-        // * JNoNu (:398-415): (len^2 I - nUn nUn^T) / len^3, evaluated on the UNflipped normal
-        const float l2 = len * len, l3 = l2 * len, un = dot(u3, nUn);
-        const V3 q = v3((l2 * u3.x - un * nUn.x) / l3, (l2 * u3.y - un * nUn.y) / l3, (l2 * u3.z - un * nUn.z) / l3);
+        // * JNoNu (:398-415): (len^2 I - nUn nUn^T) / len^3 = (u - (u.n^)n^) / len, UNflipped normal n^ = nUn/len
+        const V3 nh = ilen * nUn;
+        const float un = dot(u3, nh);
+        const V3 q = ilen * (u3 - un * nh);
         // * JNoBc * JBcVp: direct dependence of the barycentrics on the triangle's own vertices
         const float r0 = dot(q, n0), r1 = dot(q, n1), r2 = dot(q, n2);
         V3 g0, g1, g2;
-        bary_vjp(o, d, p0, p1, p2, r0 - r2, r1 - r2, g0, g1, g2);
-        val[9] = g0.x; val[10] = g0.y; val[11] = g0.z;
-        val[12] = g1.x; val[13] = g1.y; val[14] = g1.z;
-        val[15] = g2.x; val[16] = g2.y; val[17] = g2.z;
+        bary_vjp_fast(o, d, p0, p1, p2, r0 - r2, r1 - r2, g0, g1, g2);
+        pos9[0] = g0.x; pos9[1] = g0.y; pos9[2] = g0.z;
+        pos9[3] = g1.x; pos9[4] = g1.y; pos9[5] = g1.z;
+        pos9[6] = g2.x; pos9[7] = g2.y; pos9[8] = g2.z;
         // vertex-normal gradient, finished in normal_term_kernel
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { val[18 + i * 3] = bc[i] * q.x; val[19 + i * 3] = bc[i] * q.y; val[20 + i * 3] = bc[i] * q.z; }
+        for (int i = 0; i < 3; ++i) { mine[18 + i * 3] = bc[i] * q.x; mine[19 + i * 3] = bc[i] * q.y; mine[20 + i * 3] = bc[i] * q.z; }
       }
 
       // ---- model-to-data term (:531-555) ----
@@ -244,8 +282,8 @@ pixel_grad_kernel(const PixelParams p) {
               dIu = dIu + Gu * I; dIv = dIv + Gv * I;
               norm += fabsf(Gu);
             }
-          dIu = v3(dIu.x / norm, dIu.y / norm, dIu.z / norm);
-          dIv = v3(dIv.x / norm, dIv.y / norm, dIv.z / norm);
+          const float inorm = 1.f / norm;
+          dIu = inorm * dIu; dIv = inorm * dIv;
         }
         const V3 gt = ldv3(p.target_grad, pix);
         const float w0 = dot(gt, dIu), w1 = dot(gt, dIv);
@@ -260,16 +298,18 @@ pixel_grad_kernel(const PixelParams p) {
         const float Py = M[1][0] * fp.x + M[1][1] * fp.y + M[1][2] * fp.z + M[1][3];
         const float Pz = M[2][0] * fp.x + M[2][1] * fp.y + M[2][2] * fp.z + M[2][3];
         if (fabsf(Pz) > 0.0001f) {
-          const float iz = 1.f / Pz, kx = -Px / (Pz * Pz), ky = -Py / (Pz * Pz);
+          const float iz = 1.f / Pz, kx = -Px * iz * iz, ky = -Py * iz * iz;
           float w2[3];
 #pragma unroll
           for (int j = 0; j < 3; ++j) w2[j] = w0 * (iz * M[0][j] + kx * M[2][j]) + w1 * (iz * M[1][j] + ky * M[2][j]);
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) val[9 + i * 3 + j] += bc[i] * w2[j];
+            for (int j = 0; j < 3; ++j) pos9[i * 3 + j] += bc[i] * w2[j];
         }
       }
+#pragma unroll
+      for (int j = 0; j < 9; ++j) mine[9 + j] = pos9[j];
     }
 
     // ---- run-aggregated scatter: lane j owns value j ----
@@ -277,8 +317,6 @@ pixel_grad_kernel(const PixelParams p) {
     const unsigned head = __ballot_sync(FULL_MASK, covered && (lane == 0 || prevFace != face));
     const unsigned cont = (cv & ~head) >> 1;         // bit l: lane l+1 continues lane l's run
     const unsigned endm = cv & ~cont;
-#pragma unroll
-    for (int j = 0; j < kVals; ++j) mybuf[lane * kVals + j] = val[j];
     __syncwarp();
     const int arr = lane / 9, vi = (lane % 9) / 3, comp = lane % 3;
     const bool active = lane < kVals && ((arr == 0 && p.albedo == GVV_ALBEDO_VERTEX_COLOR) ||
@@ -290,7 +328,7 @@ pixel_grad_kernel(const PixelParams p) {
     while (rem) {
       const int l = __ffs(rem) - 1;
       rem &= rem - 1;
-      if (lane < kVals) acc += mybuf[l * kVals + lane];
+      if (active) acc += mybuf[l * kVals + lane];
       if ((endm >> l) & 1u) {
         const int fr = __shfl_sync(FULL_MASK, face, l);
         if (active) {
@@ -304,15 +342,19 @@ pixel_grad_kernel(const PixelParams p) {
     __syncwarp();
   }
 
-  // ---- SH gradient: warp -> block -> 27 atomics per block ----
+  // ---- SH gradient: 12 values per pixel (g*albedo, Y), lane j = (ch,k) sums gA[ch]*Y[k]; warp -> block -> 27 atomics ----
   float shsum = 0.f;
   if (shaded && cv) {
+    if (covered) {
+      mine[0] = gA[0]; mine[1] = gA[1]; mine[2] = gA[2];
 #pragma unroll
-    for (int j = 0; j < kVals; ++j) mybuf[lane * kVals + j] = shv[j];
+      for (int k = 0; k < 9; ++k) mine[3 + k] = Y[k];
+    }
     __syncwarp();
     if (lane < kVals) {
+      const int ch = lane / 9, k = lane % 9;
       unsigned rem = cv;
-      while (rem) { const int l = __ffs(rem) - 1; rem &= rem - 1; shsum += mybuf[l * kVals + lane]; }
+      while (rem) { const int l = __ffs(rem) - 1; rem &= rem - 1; shsum += mybuf[l * kVals + ch] * mybuf[l * kVals + 3 + k]; }
     }
   }
   if (lane < kVals) shPart[warp][lane] = shsum;
@@ -322,6 +364,40 @@ pixel_grad_kernel(const PixelParams p) {
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += shPart[w][tid];
     if (s != 0.f) atomicAdd(p.sh_grad + (size_t)view * 27 + tid, s);
+  }
+}
+
+// Repack of the caller's 12-byte AoS vertex arrays into aligned float4 (one 16-B gather instead of
+// three 4-B ones per vertex in pixel_grad_kernel) + zero fill of all gradient outputs.
+struct PrepArgs {
+  ZeroArgs z;
+  const float *vertex_pos, *vertex_color, *vertex_normal;
+  float4 *pos4, *col4, *nor4;
+  long long nBN, nVN;
+};
+
+__global__ void prep_kernel(PrepArgs a) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long i = t0; i < a.nBN; i += stride) {
+    a.pos4[i] = make_float4(__ldg(a.vertex_pos + 3 * i), __ldg(a.vertex_pos + 3 * i + 1), __ldg(a.vertex_pos + 3 * i + 2), 0.f);
+    if (a.vertex_color) a.col4[i] = make_float4(__ldg(a.vertex_color + 3 * i), __ldg(a.vertex_color + 3 * i + 1), __ldg(a.vertex_color + 3 * i + 2), 0.f);
+  }
+  for (long long i = t0; i < a.nVN; i += stride)
+    a.nor4[i] = make_float4(__ldg(a.vertex_normal + 3 * i), __ldg(a.vertex_normal + 3 * i + 1), __ldg(a.vertex_normal + 3 * i + 2), 0.f);
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    float* p = a.z.p[r];
+    if (!p) continue;
+    const long long n = a.z.n[r];
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      float4* p4 = reinterpret_cast<float4*>(p);
+      const long long n4 = n >> 2;
+      for (long long i = t0; i < n4; i += stride) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (long long i = (n4 << 2) + t0; i < n; i += stride) p[i] = 0.f;
+    } else {
+      for (long long i = t0; i < n; i += stride) p[i] = 0.f;
+    }
   }
 }
 
@@ -367,14 +443,20 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   z.p[2] = a.s.gnorm;   z.n[2] = nv;
   z.p[3] = a.sh_grad;   z.n[3] = (long long)V * 27;
   z.p[4] = a.tex_grad;  z.n[4] = a.tex_grad ? (long long)a.B * a.texH * a.texW * 3 : 0;
+  PrepArgs pa;
+  pa.z = z;
+  pa.vertex_pos = a.vertex_pos; pa.vertex_color = a.vertex_color; pa.vertex_normal = a.vertex_normal;
+  pa.pos4 = a.s.bpos4; pa.col4 = a.s.bcol4; pa.nor4 = a.s.bnor4;
+  pa.nBN = (long long)a.B * a.N; pa.nVN = (long long)V * a.N;
   tm->begin(K_ZERO, st);
-  zero_kernel<<<148 * 8, 256, 0, st>>>(z);
+  prep_kernel<<<148 * 8, 256, 0, st>>>(pa);
   tm->end(st);
   ++launches;
   PixelParams p;
   p.render_grad = a.render_grad; p.target_grad = a.target_grad; p.vertex_pos = a.vertex_pos; p.vertex_color = a.vertex_color;
   p.texture = a.texture; p.sh_coeff = a.sh_coeff; p.target_image = a.target_image; p.vertex_normal = a.vertex_normal;
   p.bary = a.bary; p.texcoords = a.texcoords; p.face = a.face; p.faces4 = a.faces4; p.cams = a.s.cams;
+  p.pos4 = a.s.bpos4; p.col4 = a.s.bcol4; p.nor4 = a.s.bnor4;
   p.vpos_grad = a.vpos_grad; p.vcol_grad = a.vcol_grad; p.tex_grad = a.tex_grad; p.sh_grad = a.sh_grad; p.gnorm = a.s.gnorm;
   p.C = a.C; p.N = a.N; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
   p.albedo = a.albedo; p.shading = a.shading; p.imgFilter = a.imgFilter;

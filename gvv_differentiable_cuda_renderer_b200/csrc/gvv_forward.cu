@@ -225,15 +225,62 @@ bin_fill_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj
 // ------------------------------------------------------------------------------------------------
 // raster_kernel
 // ------------------------------------------------------------------------------------------------
-struct __align__(16) TriRec {   // 24 words; read back as six float4
+// Per-(triangle, tile) records staged in shared memory.
+// TriRec: everything the exact hit test needs (five float4).
+struct __align__(16) TriRec {
   float v0x, v0y, v0z, v1x;
   float v1y, v1z, v2x, v2y;
   float v2z, Nx, Ny, Nz;
   float num, den, z0, z1;
-  float z2; int face; int start; int x0y0;
-  int w; int rcpw; int pad0; int pad1;
+  float z2; int face; int pad0; int pad1;
 };
-static_assert(sizeof(TriRec) == 96, "TriRec is 96 bytes");
+static_assert(sizeof(TriRec) == 80, "TriRec is 80 bytes");
+// EdgeRec: fragment decode + the conservative screen-space pre-test (three float4).
+struct __align__(16) EdgeRec {
+  float A0, B0, C0, A1;
+  float B1, C1, A2, B2;
+  float C2; int start; int geom; int rcpw;   // geom = x0 | y0 << 8 | w << 16 (tile-local)
+};
+static_assert(sizeof(EdgeRec) == 48, "EdgeRec is 48 bytes");
+
+// Conservative screen-space reject.  The reference tests EVERY pixel of the bbox with the exact
+// 3-D test; a pair that fails it has no effect at all, so pairs that provably fail may be skipped.
+// Under the pinhole map the 3-D triangle projects exactly onto the 2-D triangle of the projected
+// vertices, and the reference's inside test admits perspective barycentrics >= -0.001, i.e. screen
+// distances up to 0.001 * (zmax/zmin) * height outside an edge.  We keep every pixel centre within
+//     m = 0.25 px + 0.002 * (zmax/zmin) * (longest edge)      (>= 2x that bound + 0.25 px for rounding)
+// of the triangle and send it to the exact test; only pixels farther out are dropped.  Triangles
+// whose projection is unreliable (a vertex at/behind the camera plane, depth ratio > 2, non-finite
+// coordinates) are not culled at all; thin triangles (|area| < 1 px^2, orientation ambiguous) use a
+// two-sided band around their longest edge.  e_i(lx,ly) = A_i*lx + B_i*ly + C_i >= 0 keeps the pixel.
+__device__ __forceinline__ void edge_setup(float4 p0, float4 p1, float4 p2, float ox, float oy, float margin, EdgeRec& e) {
+  const float x0 = p0.x - ox, y0 = p0.y - oy, x1 = p1.x - ox, y1 = p1.y - oy, x2 = p2.x - ox, y2 = p2.y - oy;
+  const float zmin = fminf(p0.z, fminf(p1.z, p2.z)), zmax = fmaxf(p0.z, fmaxf(p1.z, p2.z));
+  e.A0 = e.B0 = e.A1 = e.B1 = e.A2 = e.B2 = 0.f;
+  e.C0 = e.C1 = e.C2 = 1.f;                                   // default: keep everything
+  if (!(margin >= 0.f) || !(zmin > 1.0e-4f) || !(zmax <= 2.f * zmin)) return;   // margin < 0: culling off
+  const float ax = x1 - x0, ay = y1 - y0, bx = x2 - x1, by = y2 - y1, cx = x0 - x2, cy = y0 - y2;
+  const float area2 = ax * (y2 - y0) - ay * (x2 - x0);
+  const float la = sqrtf(ax * ax + ay * ay), lb = sqrtf(bx * bx + by * by), lc = sqrtf(cx * cx + cy * cy);
+  const float lmax = fmaxf(la, fmaxf(lb, lc));
+  const float m = margin + 0.002f * (zmax / zmin) * lmax;
+  if (!(lmax < 1.0e6f) || !(fabsf(area2) < 1.0e12f)) return;   // also rejects NaN / inf
+  // E(x,y) = dx*(y - ya) - dy*(x - xa) for the edge a->b: A = -dy, B = dx, C = dy*xa - dx*ya; pixel centre = (lx+.5, ly+.5)
+  if (fabsf(area2) >= 1.f) {
+    const float s = area2 > 0.f ? 1.f : -1.f;
+    e.A0 = -s * ay; e.B0 = s * ax; e.C0 = s * (ay * x0 - ax * y0) + 0.5f * (e.A0 + e.B0) + m * la;
+    e.A1 = -s * by; e.B1 = s * bx; e.C1 = s * (by * x1 - bx * y1) + 0.5f * (e.A1 + e.B1) + m * lb;
+    e.A2 = -s * cy; e.B2 = s * cx; e.C2 = s * (cy * x2 - cx * y2) + 0.5f * (e.A2 + e.B2) + m * lc;
+  } else {
+    // thin: |E_long| <= |area2| inside the triangle, so keep |E_long| <= |area2| + m*len
+    float dx = ax, dy = ay, xa = x0, ya = y0, len = la;
+    if (lb >= la && lb >= lc) { dx = bx; dy = by; xa = x1; ya = y1; len = lb; }
+    else if (lc >= la && lc >= lb) { dx = cx; dy = cy; xa = x2; ya = y2; len = lc; }
+    const float A = -dy, B = dx, C = dy * xa - dx * ya + 0.5f * (A + B), T = fabsf(area2) + m * len;
+    e.A0 = A; e.B0 = B; e.C0 = C + T;
+    e.A1 = -A; e.B1 = -B; e.C1 = -C + T;
+  }
+}
 
 struct RasterParams {
   const int4* faces4; const float4* proj; const float4* vscaled; const float4* vnorm4; const float4* vcol4;
@@ -242,6 +289,7 @@ struct RasterParams {
   const float* texture; const float* texcoords; const float* sh_coeff;
   float* bary; int32_t* face; float* render;
   int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT;
+  float cullMargin;
 };
 
 __device__ __forceinline__ TriSetup load_setup(const RasterParams& p, int b, int view, int4 fc, F3 ros,
@@ -270,15 +318,18 @@ __device__ __forceinline__ float sh_eval(const float* __restrict__ sh, F3 n) {
 }
 
 template <int TS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 raster_kernel(const RasterParams p) {
   constexpr int NPIX = TS * TS;
-  constexpr int CHUNK = 256;
+  constexpr int CHUNK = 128;
   constexpr int SHIFT = 21;
+  constexpr int QCAP = 64;            // per-warp survivor ring (power of two, >= 2*32)
   __shared__ unsigned long long zt[NPIX];
   __shared__ float rayx[NPIX], rayy[NPIX], rayz[NPIX];
   __shared__ TriRec rec[CHUNK];
+  __shared__ EdgeRec erec[CHUNK];
   __shared__ int startArr[CHUNK + 40];
+  __shared__ int queue[8][QCAP];
   __shared__ int warpTot[8];
   __shared__ float shc[27];
   __shared__ CamRec cam;
@@ -319,33 +370,67 @@ raster_kernel(const RasterParams p) {
     rayx[q] = rd.x; rayy[q] = rd.y; rayz[q] = rd.z;
   }
 
+  // exact test + 64-bit atomicMin for up to 32 queued (triangle, pixel) pairs
+  int* myq = queue[warp];
+  auto drain = [&](int head, int n) {
+    if (lane < n) {
+      const int ent = myq[(head + lane) & (QCAP - 1)];
+      const int k = ent >> 10, q = ent & 1023;
+      const float4* rp = reinterpret_cast<const float4*>(&rec[k]);
+      const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3];
+      const int4 r4 = reinterpret_cast<const int4*>(rp)[4];
+      TriSetup ts;
+      ts.v0 = mk3(r0.x, r0.y, r0.z); ts.v1 = mk3(r0.w, r1.x, r1.y); ts.v2 = mk3(r1.z, r1.w, r2.x);
+      ts.N = mk3(r2.y, r2.z, r2.w); ts.num = r3.x; ts.den = r3.y;
+      const F3 rd = mk3(rayx[q], rayy[q], rayz[q]);
+      float a, bq, c;
+      if (hit_exact(ts, ros, rd, a, bq, c)) {
+        const int depth = depth_key_exact(a, bq, c, r3.z, r3.w, __int_as_float(r4.x));
+        const unsigned long long key = pack_key(depth, r4.y);
+        unsigned long long cur = zt[q];
+        while (key < cur) {                     // 64-bit atomicMin on the shared z-tile
+          const unsigned long long old = atomicCAS(&zt[q], cur, key);
+          if (old == cur) break;
+          cur = old;
+        }
+      }
+    }
+  };
+
   // ---- rasterise: the tile's own bin, then the view's big-triangle list ----
   for (int pass = 0; pass < 2; ++pass) {
     const int cnt = pass == 0 ? cntSmall : cntBig;
     const int* list = pass == 0 ? p.bins + (size_t)view * p.F * kMaxSmallTiles + p.tileOffset[tidx]
                                 : p.bigList + (size_t)view * p.F;
     for (int chunk = 0; chunk < cnt; chunk += CHUNK) {
-      __syncthreads();   // rec/startArr of the previous chunk (and the z-tile clear) are done
+      __syncthreads();   // rec/erec/startArr of the previous chunk (and the z-tile clear) are done
       const int i = chunk + tid;
       int n = 0;
       TriRec mine;
-      if (i < cnt) {
+      EdgeRec em;
+      if (tid < CHUNK && i < cnt) {
         const int f = __ldg(list + i);
         const int4 fc = __ldg(p.faces4 + f);
-        float z0, z1, z2; int4 bb;
-        const TriSetup ts = load_setup(p, b, view, fc, ros, z0, z1, z2, &bb);
+        const float4* vs = p.vscaled + (size_t)b * p.N;
+        const float4* pj = p.proj + (size_t)view * p.N;
+        const float4 s0 = __ldg(vs + fc.x), s1 = __ldg(vs + fc.y), s2 = __ldg(vs + fc.z);
+        const float4 p0 = __ldg(pj + fc.x), p1 = __ldg(pj + fc.y), p2 = __ldg(pj + fc.z);
+        const int4 bb = bbox_exact(p0, p1, p2, p.W, p.H);
         const int cx0 = max(bb.x, tileX0), cx1 = min(bb.z, tileX0 + TS - 1);
         const int cy0 = max(bb.y, tileY0), cy1 = min(bb.w, tileY0 + TS - 1);
         const int w = cx1 - cx0 + 1, h = cy1 - cy0 + 1;
         if (w > 0 && h > 0) {
           n = w * h;
+          const TriSetup ts = tri_setup_exact(mk3(s0.x, s0.y, s0.z), mk3(s1.x, s1.y, s1.z), mk3(s2.x, s2.y, s2.z), ros);
           mine.v0x = ts.v0.x; mine.v0y = ts.v0.y; mine.v0z = ts.v0.z;
           mine.v1x = ts.v1.x; mine.v1y = ts.v1.y; mine.v1z = ts.v1.z;
           mine.v2x = ts.v2.x; mine.v2y = ts.v2.y; mine.v2z = ts.v2.z;
           mine.Nx = ts.N.x; mine.Ny = ts.N.y; mine.Nz = ts.N.z;
-          mine.num = ts.num; mine.den = ts.den; mine.z0 = z0; mine.z1 = z1; mine.z2 = z2;
-          mine.face = f; mine.x0y0 = (cx0 - tileX0) | ((cy0 - tileY0) << 16);
-          mine.w = w; mine.rcpw = ((1 << 18) + w - 1) / w; mine.pad0 = 0; mine.pad1 = 0;
+          mine.num = ts.num; mine.den = ts.den; mine.z0 = p0.z; mine.z1 = p1.z; mine.z2 = p2.z;
+          mine.face = f; mine.pad0 = 0; mine.pad1 = 0;
+          edge_setup(p0, p1, p2, (float)tileX0, (float)tileY0, p.cullMargin, em);
+          em.geom = (cx0 - tileX0) | ((cy0 - tileY0) << 8) | (w << 16);
+          em.rcpw = ((1 << 18) + w - 1) / w;
         }
       }
       // block-wide exclusive scan of (1 << SHIFT | n): rank among non-empty triangles + first fragment
@@ -362,9 +447,10 @@ raster_kernel(const RasterParams p) {
       const int ntri = total >> SHIFT, nfrag = total & ((1 << SHIFT) - 1);
       if (n > 0) {
         const int rank = excl >> SHIFT;
-        mine.start = excl & ((1 << SHIFT) - 1);
+        em.start = excl & ((1 << SHIFT) - 1);
         rec[rank] = mine;
-        startArr[rank] = mine.start;
+        erec[rank] = em;
+        startArr[rank] = em.start;
       }
       if (tid < 40) startArr[ntri + tid] = 0x7fffffff;
       __syncthreads();
@@ -377,6 +463,7 @@ raster_kernel(const RasterParams p) {
         int c0 = 0;
         for (int j = lane; j < ntri; j += 32) c0 += (startArr[j] <= lo) ? 1 : 0;
         int K0 = __reduce_add_sync(FULL_MASK, c0) - 1;   // triangle containing fragment `lo`
+        int qhead = 0, qcount = 0;
         for (int fb = lo; fb < hi; fb += 32) {
           const int s = startArr[K0 + 1 + lane];
           const unsigned bits = (s < fb + 32) ? (1u << (s - fb)) : 0u;
@@ -384,32 +471,35 @@ raster_kernel(const RasterParams p) {
           const int k = K0 + __popc(mask & ((2u << lane) - 1u));
           K0 += __popc(mask);
           const int fr = fb + lane;
+          bool keep = false;
+          int ent = 0;
           if (fr < hi) {
-            const float4* rp = reinterpret_cast<const float4*>(&rec[k]);
-            const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3];
-            const int4 r4 = reinterpret_cast<const int4*>(rp)[4];
-            const int4 r5 = reinterpret_cast<const int4*>(rp)[5];
-            const int local = fr - r4.z;
-            const int dy = (int)(((unsigned)local * (unsigned)r5.y) >> 18);
-            const int dx = local - dy * r5.x;
-            const int q = ((r4.w >> 16) + dy) * TS + (r4.w & 0xffff) + dx;
-            TriSetup ts;
-            ts.v0 = mk3(r0.x, r0.y, r0.z); ts.v1 = mk3(r0.w, r1.x, r1.y); ts.v2 = mk3(r1.z, r1.w, r2.x);
-            ts.N = mk3(r2.y, r2.z, r2.w); ts.num = r3.x; ts.den = r3.y;
-            const F3 rd = mk3(rayx[q], rayy[q], rayz[q]);
-            float a, bq, c;
-            if (hit_exact(ts, ros, rd, a, bq, c)) {
-              const int depth = depth_key_exact(a, bq, c, r3.z, r3.w, __int_as_float(r4.x));
-              const unsigned long long key = pack_key(depth, r4.y);
-              unsigned long long cur = zt[q];
-              while (key < cur) {                     // 64-bit atomicMin on the shared z-tile
-                const unsigned long long old = atomicCAS(&zt[q], cur, key);
-                if (old == cur) break;
-                cur = old;
-              }
-            }
+            const float4* ep = reinterpret_cast<const float4*>(&erec[k]);
+            const float4 e0 = ep[0], e1 = ep[1];
+            const int4 e2 = reinterpret_cast<const int4*>(ep)[2];
+            const int local = fr - e2.y;
+            const int w = e2.z >> 16;
+            const int dy = (int)(((unsigned)local * (unsigned)e2.w) >> 18);
+            const int lx = (e2.z & 0xff) + local - dy * w, ly = ((e2.z >> 8) & 0xff) + dy;
+            const float fx = (float)lx, fy = (float)ly;
+            const float t0 = fmaf(e0.x, fx, fmaf(e0.y, fy, e0.z));
+            const float t1 = fmaf(e0.w, fx, fmaf(e1.x, fy, e1.y));
+            const float t2 = fmaf(e1.z, fx, fmaf(e1.w, fy, __int_as_float(e2.x)));
+            keep = fminf(t0, fminf(t1, t2)) >= 0.f;
+            ent = (k << 10) | (ly * TS + lx);
+          }
+          const unsigned km = __ballot_sync(FULL_MASK, keep);
+          if (keep) myq[(qhead + qcount + __popc(km & ((1u << lane) - 1u))) & (QCAP - 1)] = ent;
+          qcount += __popc(km);
+          __syncwarp();
+          if (qcount >= 32) {
+            drain(qhead, 32);
+            qhead = (qhead + 32) & (QCAP - 1);
+            qcount -= 32;
+            __syncwarp();
           }
         }
+        if (qcount > 0) { drain(qhead, qcount); __syncwarp(); }
       }
     }
   }
@@ -513,6 +603,13 @@ int launch_camera(const float* extr, const float* intr, CamRec* cams, int* bigCo
   return 1;
 }
 
+int launch_vertex(const FwdArgs& a, cudaStream_t st) {
+  vertex_kernel<<<dim3((a.N + 127) / 128, a.B), 128, 0, st>>>(a.vertex_pos, a.vertex_color, a.faces4, a.vfOffsets, a.vfList,
+                                                             a.s.cams, a.s.proj, a.s.vscaled, a.s.vnorm4, a.s.vcol4,
+                                                             a.vertex_normal, a.N, a.C);
+  return 1;
+}
+
 int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const int V = a.B * a.C;
   tm->begin(K_CAMERA, st);
@@ -557,7 +654,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   p.texture = a.texture; p.texcoords = a.texcoords; p.sh_coeff = a.sh_coeff;
   p.bary = a.bary; p.face = a.face; p.render = a.render;
   p.C = a.C; p.N = a.N; p.F = a.F; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
-  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT;
+  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin;
   const dim3 gridT(a.nT, V);
   tm->begin(K_RASTER, st);
   if (a.tile == 16) raster_kernel<16><<<gridT, 256, 0, st>>>(p);

@@ -27,6 +27,9 @@ struct Scratch {
   int* bigList = nullptr;        // [V*F]
   int* bins = nullptr;           // [V*F*kMaxSmallTiles]
   float* gnorm = nullptr;        // [B*N*3] backward: dL/d(unnormalised vertex normal)
+  float4* bpos4 = nullptr;       // [B*N]  backward: repacked vertex_pos (raw)
+  float4* bcol4 = nullptr;       // [B*N]  backward: repacked vertex_color
+  float4* bnor4 = nullptr;       // [V*N]  backward: repacked vertex_normal input
 };
 
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py roofline leg).
@@ -53,6 +56,7 @@ struct gvv_renderer {
   int F = 0, N = 0, C = 0, W = 0, H = 0;
   int albedo = 0, shading = 0, imgFilter = 1, texFilter = 1, computeNormalMap = 0;
   int tile = 32, tilesX = 0, tilesY = 0, nT = 0;
+  float cullMargin = 0.25f;   // px; < 0 disables the conservative screen-space pre-test
   bool hasTexcoords = false;
   int4* faces4 = nullptr;     // [F] (v0,v1,v2,0)
   float* texcoords = nullptr; // [F*6]
@@ -70,6 +74,7 @@ namespace gvv {
 struct FwdArgs {
   int B, C, N, F, W, H, texH, texW, albedo, shading;
   int tile, tilesX, tilesY, nT;
+  float cullMargin;
   const float *vertex_pos, *vertex_color, *texture, *sh_coeff, *extrinsics, *intrinsics;
   const float* texcoords;
   const int4* faces4;

@@ -134,7 +134,10 @@ int64_t gvv_debug_copy(gvv_handle h, int32_t which, void* host_dst, int64_t capa
  * fails the inside test; out_ab: HOST float[n*2] barycentrics (a,b).  Synchronises `stream`. */
 int gvv_debug_eval(gvv_handle h, int32_t n, const int32_t* queries, int32_t* out_key, float* out_ab, void* stream);
 
-/* Runtime knobs: key "tile" (16|32 rasteriser tile edge; default 32); key "time_kernels" (1: record
+/* Runtime knobs: key "tile" (16|32 rasteriser tile edge; default 32); key "cull_margin_milli" (fixed
+ * part, in 1/1000 pixel, of the margin of the conservative screen-space pre-test that decides which
+ * bbox pixels get the exact test; default 250; negative = test every bbox pixel exactly, like the
+ * reference -- results are identical either way, see tests); key "time_kernels" (1: record
  * a CUDA-event pair around every kernel on the launching stream, 0: off; either resets the log).
  * Returns 0 on success. */
 int gvv_set_option(gvv_handle h, const char* key, int32_t value);

@@ -189,6 +189,14 @@ def test_headline_size_properties(headline):
     out3 = r16.forward(*ins)
     for a, b in zip(out1[:4], out3[:4]):                       # tiling changes who evaluates, never what
         assert torch.equal(a.view(torch.int32) if a.dtype == torch.float32 else a, b.view(torch.int32) if b.dtype == torch.float32 else b)
+    # the conservative screen-space pre-test only skips pairs that fail the exact test anyway:
+    # identical bits with it switched off (every bbox pixel tested, like the reference) or tightened
+    for margin in (-1, 16):
+        rc = make(sc, "vertexColor", "shaded", 32)
+        rc.set_option("cull_margin_milli", margin)
+        for a, b in zip(out1[:4], rc.forward(*ins)[:4]):
+            assert torch.equal(a.view(torch.int32) if a.dtype == torch.float32 else a, b.view(torch.int32) if b.dtype == torch.float32 else b)
+        rc.close()
     bary, face, render, vn = out1[:4]
     cov = float((face >= 0).float().mean())
     assert 0.45 < cov < 0.60                                   # ~50 % coverage, as the workload is specified
