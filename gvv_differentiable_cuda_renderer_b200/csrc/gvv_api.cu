@@ -39,7 +39,7 @@ static cudaError_t dmalloc(T** p, size_t count) {
 
 static void free_scratch(Scratch& s) {
   cudaFree(s.cams); cudaFree(s.proj); cudaFree(s.vscaled); cudaFree(s.vnorm4); cudaFree(s.vcol4);
-  cudaFree(s.tileCount); cudaFree(s.tileCursor); cudaFree(s.tileOffset); cudaFree(s.bigCount);
+  cudaFree(s.tileCount); cudaFree(s.tileCursor); cudaFree(s.tileOffset); cudaFree(s.tileOrder); cudaFree(s.bigCount);
   cudaFree(s.bigList); cudaFree(s.bins); cudaFree(s.gnorm); cudaFree(s.bpos4); cudaFree(s.bcol4); cudaFree(s.bnor4);
   s = Scratch();
 }
@@ -69,6 +69,7 @@ static int ensure_scratch(gvv_renderer* h, int B, cudaStream_t st) {
   acc(dmalloc(&s.tileCount, (size_t)V * nT));
   acc(dmalloc(&s.tileCursor, (size_t)V * nT));
   acc(dmalloc(&s.tileOffset, (size_t)V * nT));
+  acc(dmalloc(&s.tileOrder, (size_t)V * nT));
   acc(dmalloc(&s.bigCount, (size_t)V));
   acc(dmalloc(&s.bigList, (size_t)V * F));
   acc(dmalloc(&s.bins, (size_t)V * F * kMaxSmallTiles));

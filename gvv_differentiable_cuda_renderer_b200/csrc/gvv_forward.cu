@@ -147,10 +147,14 @@ bin_count_kernel(const int4* __restrict__ faces4, const float4* __restrict__ pro
   }
 }
 
-// exclusive scan of one view's tile histogram (one block per view)
-__global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ tileCount, int* __restrict__ tileOffset, int nT) {
+// exclusive scan of one view's tile histogram (one block per view) + the order in which the raster
+// CTAs visit the tiles: heaviest bins first (longest-processing-time-first keeps the silhouette
+// tiles, which hold ~10x the average work, out of the tail of the launch)
+__global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ tileCount, int* __restrict__ tileOffset,
+                                                        int* __restrict__ tileOrder, int nT) {
   __shared__ int warpSum[32];
   __shared__ int carry;
+  __shared__ int bucketStart[33], bucketFill[33];
   const int view = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry = 0;
@@ -175,6 +179,24 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
     __syncthreads();
     if (threadIdx.x == 0) carry += warpSum[31];
     __syncthreads();
+  }
+  // counting sort of the tiles by floor(log2(count)) (33 buckets, 32 = heaviest ... 0 = empty)
+  if (threadIdx.x < 33) { bucketStart[threadIdx.x] = 0; bucketFill[threadIdx.x] = 0; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nT; i += blockDim.x) {
+    const int c = tileCount[(size_t)view * nT + i];
+    atomicAdd(&bucketStart[c > 0 ? 32 - __clz(c) : 0], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int k = 32; k >= 0; --k) { const int c = bucketStart[k]; bucketStart[k] = run; run += c; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nT; i += blockDim.x) {
+    const int c = tileCount[(size_t)view * nT + i];
+    const int k = c > 0 ? 32 - __clz(c) : 0;
+    tileOrder[(size_t)view * nT + bucketStart[k] + atomicAdd(&bucketFill[k], 1)] = i;
   }
 }
 
@@ -285,10 +307,10 @@ __device__ __forceinline__ void edge_setup(float4 p0, float4 p1, float4 p2, floa
 struct RasterParams {
   const int4* faces4; const float4* proj; const float4* vscaled; const float4* vnorm4; const float4* vcol4;
   const CamRec* cams;
-  int* tileCount; int* tileCursor; const int* tileOffset; const int* bigCount; const int* bigList; const int* bins;
+  int* tileCount; int* tileCursor; const int* tileOffset; const int* tileOrder; const int* bigCount; const int* bigList; const int* bins;
   const float* texture; const float* texcoords; const float* sh_coeff;
   float* bary; int32_t* face; float* render;
-  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT;
+  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, V;
   float cullMargin;
 };
 
@@ -334,7 +356,9 @@ raster_kernel(const RasterParams p) {
   __shared__ float shc[27];
   __shared__ CamRec cam;
 
-  const int tile = blockIdx.x, view = blockIdx.y;
+  // 1-D grid, view fastest: the heaviest tiles of every view are scheduled first
+  const int view = blockIdx.x % p.V;
+  const int tile = p.tileOrder[(size_t)view * p.nT + blockIdx.x / p.V];
   const int b = view / p.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tileX0 = (tile % p.tilesX) * TS, tileY0 = (tile / p.tilesX) * TS;
@@ -634,7 +658,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   tm->end(st);
   ++launches;
   tm->begin(K_BIN_SCAN, st);
-  bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.nT);
+  bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.nT);
   tm->end(st);
   ++launches;
   tm->begin(K_BIN_FILL, st);
@@ -649,13 +673,13 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   ++launches;
   RasterParams p;
   p.faces4 = a.faces4; p.proj = a.s.proj; p.vscaled = a.s.vscaled; p.vnorm4 = a.s.vnorm4; p.vcol4 = a.s.vcol4;
-  p.cams = a.s.cams; p.tileCount = a.s.tileCount; p.tileCursor = a.s.tileCursor; p.tileOffset = a.s.tileOffset;
+  p.cams = a.s.cams; p.tileCount = a.s.tileCount; p.tileCursor = a.s.tileCursor; p.tileOffset = a.s.tileOffset; p.tileOrder = a.s.tileOrder; p.V = V;
   p.bigCount = a.s.bigCount; p.bigList = a.s.bigList; p.bins = a.s.bins;
   p.texture = a.texture; p.texcoords = a.texcoords; p.sh_coeff = a.sh_coeff;
   p.bary = a.bary; p.face = a.face; p.render = a.render;
   p.C = a.C; p.N = a.N; p.F = a.F; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
   p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin;
-  const dim3 gridT(a.nT, V);
+  const dim3 gridT((unsigned)a.nT * (unsigned)V);
   tm->begin(K_RASTER, st);
   if (a.tile == 16) raster_kernel<16><<<gridT, 256, 0, st>>>(p);
   else raster_kernel<32><<<gridT, 256, 0, st>>>(p);

@@ -23,6 +23,7 @@ struct Scratch {
   int* tileCount = nullptr;      // [V*nT] self-cleaning (the raster kernel zeroes its own entry)
   int* tileCursor = nullptr;     // [V*nT] self-cleaning
   int* tileOffset = nullptr;     // [V*nT]
+  int* tileOrder = nullptr;      // [V*nT] tiles of a view sorted by bin size, heaviest first
   int* bigCount = nullptr;       // [V]    zeroed by camera_kernel of the next call
   int* bigList = nullptr;        // [V*F]
   int* bins = nullptr;           // [V*F*kMaxSmallTiles]

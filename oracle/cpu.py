@@ -72,6 +72,24 @@ def forward(faces, texcoords, N, C, W, H, albedo, shading, vertex_pos, vertex_co
                 fragments=int(frag))
 
 
+def normal_map(faces, texcoords, N, C, vertex_pos, tex_h, tex_w):
+    """compute_normal_map path.  Returns dict(normal_map [B,texH,texW,3], vertex_normal, covered, tie)."""
+    L = _load()
+    vp, i = ctypes.c_void_p, ctypes.c_int
+    L.gvvo_normal_map.argtypes = [vp, i, vp, i, i, i, i, i, vp, vp, vp, vp, vp]
+    L.gvvo_normal_map.restype = i
+    f = _c(np.asarray(faces).reshape(-1), np.int32)
+    t = _c(np.asarray(texcoords).reshape(-1), np.float32)
+    pos = _c(vertex_pos, np.float32)
+    B = pos.shape[0]
+    vn = np.zeros((B, C, N, 3), np.float32)
+    nm = np.zeros((B, tex_h, tex_w, 3), np.float32)
+    cov = np.zeros((tex_h, tex_w), np.uint8)
+    tie = np.zeros((tex_h, tex_w), np.uint8)
+    L.gvvo_normal_map(_p(f), f.size // 3, _p(t), N, C, B, tex_h, tex_w, _p(pos), _p(vn), _p(nm), _p(cov), _p(tie))
+    return dict(normal_map=nm, vertex_normal=vn, covered=cov, tie=tie)
+
+
 def backward(faces, texcoords, N, C, W, H, albedo, shading, image_filter, render_grad, target_grad, vertex_pos,
              vertex_color, texture, sh_coeff, target_image, vertex_normal, bary, face, extrinsics, intrinsics, nthreads=0):
     """Returns (vertex_pos_grad, vertex_color_grad, texture_grad, sh_coeff_grad)."""

@@ -537,6 +537,73 @@ int gvvo_backward(const int* faces, int F, const float* texcoords, int N, int C,
   return 0;
 }
 
+// UV-space normal map (compute_normal_map): host rasterisation of every triangle in texture space
+// (CUDABasedRasterization.cpp:237-298, rayTriangleIntersectHost :156-235) + renderNormalMapDevice
+// (CUDABasedRasterization.cu:415-445).  Faces are visited in ascending order and later faces
+// overwrite earlier ones (the reference's OpenMP loop is racy where UV triangles overlap; this is
+// its serial order).  Also writes vertex_normal [B,C,N,3] like the forward.  covered (may be null):
+// uint8 [texH,texW], 1 where some face covers the texel; tie: 1 where more than one face does.
+int gvvo_normal_map(const int* faces, int F, const float* texcoords, int N, int C, int B, int texH, int texW,
+                    const float* vertex_pos, float* vertex_normal, float* normal_map, unsigned char* covered, unsigned char* tie) {
+  Mesh mesh(faces, F, texcoords, N);
+  std::vector<float> table((size_t)texH * texW * 4, 0.f);   // (face, a, b, c), initial (0,0,0,0) (:250)
+  std::vector<int> hits((size_t)texH * texW, 0);
+  for (int f = 0; f < F; ++f) {
+    const float* t = texcoords + 6 * (long)f;
+    const V3 t0 = {texW * t[0], texH * (1.f - t[1]), 0.f}, t1 = {texW * t[2], texH * (1.f - t[3]), 0.f}, t2 = {texW * t[4], texH * (1.f - t[5]), 0.f};
+    const int xMin = (int)std::fmax(std::fmin(t0.x, std::fmin(t1.x, t2.x)) - 2, 0), xMax = (int)std::fmin(std::fmax(t0.x, std::fmax(t1.x, t2.x)) + 2, texW);
+    const int yMin = (int)std::fmax(std::fmin(t0.y, std::fmin(t1.y, t2.y)) - 2, 0), yMax = (int)std::fmin(std::fmax(t0.y, std::fmax(t1.y, t2.y)) + 2, texH);
+    for (int x = xMin; x < xMax; ++x)
+      for (int y = yMin; y < yMax; ++y) {
+        const V3 d = {0.f, 0.f, -1.f};
+        const V3 v0 = t0 / 1000.f, v1 = t1 / 1000.f, v2 = t2 / 1000.f, orig = V3{x + 0.5f, y + 0.5f, 1.f} / 1000.f;
+        const V3 Nn = cross(v1 - v0, v2 - v0);
+        const float nd = dot(d, Nn);
+        if (std::fabs(nd) < 0.0000001f) continue;
+        const float tt = (dot(v0, Nn) - dot(orig, Nn)) / nd;
+        if (tt < 0) continue;
+        const V3 P = orig + tt * d;
+        if (dot(Nn, cross(v1 - v0, P - v0)) < 0) continue;
+        float a = dot(Nn, cross(v2 - v1, P - v1));
+        if (a < 0) continue;
+        float b = dot(Nn, cross(v0 - v2, P - v2));
+        if (b < 0) continue;
+        const float den = dot(Nn, Nn);
+        a /= den; b /= den;
+        float* o = &table[((size_t)y * texW + x) * 4];
+        o[0] = (float)f; o[1] = a; o[2] = b; o[3] = 1.f - a - b;
+        hits[(size_t)y * texW + x]++;
+      }
+  }
+  for (int b = 0; b < B; ++b) {
+    const float* pos = vertex_pos + (long)b * N * 3;
+    std::vector<V3> vn(N);
+    for (int n = 0; n < N; ++n) {
+      V3 s = {0.f, 0.f, 0.f};
+      for (int i = mesh.vfOff[n]; i < mesh.vfOff[n + 1]; ++i) {
+        const int f = mesh.vfList[i];
+        const V3 v0 = ld3(pos, faces[3 * f]), v1 = ld3(pos, faces[3 * f + 1]), v2 = ld3(pos, faces[3 * f + 2]);
+        const V3 fn = cross(v1 - v0, v2 - v0);
+        s = (i == mesh.vfOff[n]) ? fn : s + fn;
+      }
+      vn[n] = s;
+      for (int c = 0; c < C; ++c) { float* o = vertex_normal + (((long)b * C + c) * N + n) * 3; o[0] = s.x; o[1] = s.y; o[2] = s.z; }
+    }
+    for (long i = 0; i < (long)texH * texW; ++i) {
+      const float* info = &table[i * 4];
+      const int idf = (int)info[0];
+      V3 n = vn[faces[3 * idf]] * info[1] + vn[faces[3 * idf + 1]] * info[2] + vn[faces[3 * idf + 2]] * info[3];
+      const float len = std::sqrt(dot(n, n));
+      if (len != 0.f) n = n / len;
+      float* o = normal_map + ((long)b * texH * texW + i) * 3;
+      o[0] = (n.x + 1.f) / 2.f; o[1] = (n.y + 1.f) / 2.f; o[2] = (n.z + 1.f) / 2.f;
+    }
+  }
+  if (covered) for (size_t i = 0; i < hits.size(); ++i) covered[i] = hits[i] > 0;
+  if (tie) for (size_t i = 0; i < hits.size(); ++i) tie[i] = hits[i] > 1;
+  return 0;
+}
+
 int gvvo_max_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -252,6 +252,25 @@ def test_finite_differences_of_linear_inputs_gpu(albedo):
     r.close()
 
 
+def test_uv_space_normal_map_matches_cpu_oracle():
+    """compute_normal_map: rasterisation is replaced by the UV-space normal map."""
+    from oracle import cpu
+    sc = synthetic.make_scene(kind="sphere", rings=14, segments=18, cameras=2, width=32, height=32, batch=2, tex=96, seed=9)
+    N, C = sc["num_vertices"], sc["num_cameras"]
+    r = _native.NativeRenderer(sc["faces"], sc["texcoords"], N, C, 32, 32, "textured", "shaded", 1, 1, True, dev())
+    ins = [T(sc[k]) for k in INPUT_KEYS]
+    bary, face, render, vn, _, nmap = r.forward(*ins)
+    o = cpu.normal_map(sc["faces"], sc["texcoords"], N, C, sc["vertex_pos"], 96, 96)
+    assert nmap.shape == (2, 96, 96, 3) and int((face >= 0).sum()) == 0        # no rasterisation in this mode
+    assert np.abs(vn.cpu().numpy() - o["vertex_normal"]).max() <= 1e-5 * np.abs(o["vertex_normal"]).max()
+    # texels covered by exactly one UV triangle are unambiguous; shared UV edges may pick either neighbour
+    clean = (o["tie"] == 0)
+    d = np.abs(nmap.cpu().numpy() - o["normal_map"])[:, clean]
+    assert d.max() <= 2e-4, float(d.max())
+    assert clean.mean() > 0.8 and o["covered"].mean() > 0.5
+    r.close()
+
+
 def test_edge_cases():
     # fully off-screen mesh, degenerate triangle, non-multiple-of-tile resolution, isolated vertex
     verts = np.array([[0, 0, 0], [50, 0, 0], [0, 50, 0], [10, 10, 10], [10, 10, 10], [999, 999, 999]], np.float32)
