@@ -73,7 +73,7 @@ static int ensure_scratch(gvv_renderer* h, int B, cudaStream_t st) {
   acc(dmalloc(&s.bigCount, (size_t)V));
   acc(dmalloc(&s.bigList, (size_t)V * F));
   acc(dmalloc(&s.bins, (size_t)V * F * kMaxSmallTiles));
-  acc(dmalloc(&s.gnorm, (size_t)B * N * 3));
+  acc(dmalloc(&s.gnorm, (size_t)B * N * 4));
   acc(dmalloc(&s.bpos4, (size_t)B * N));
   acc(dmalloc(&s.bcol4, (size_t)B * N));
   acc(dmalloc(&s.bnor4, (size_t)V * N));

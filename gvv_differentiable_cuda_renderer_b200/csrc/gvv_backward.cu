@@ -15,8 +15,8 @@
 //                        the reference loops over every face incident to the pixel's three
 //                        vertices (27*deg atomics per pixel); that sum is linear in the per-pixel
 //                        factor q, so we scatter Gn[v_i] += bcc_i*q per pixel and apply the
-//                        cross-product Jacobians (RendererUtil.h:422-539) once per vertex here,
-//                        as a gather over the CSR -- no atomics, same mathematics.
+//                        cross-product Jacobians (RendererUtil.h:422-539) once per TRIANGLE here
+//                        (9 atomics per triangle that received any gradient) -- same mathematics.
 #include "gvv_internal.h"
 
 namespace gvv {
@@ -322,21 +322,22 @@ pixel_grad_kernel(const PixelParams p) {
     const bool active = lane < kVals && ((arr == 0 && p.albedo == GVV_ALBEDO_VERTEX_COLOR) ||
                                          (arr == 1 && (shaded || p.target_grad)) || (arr == 2 && shaded));
     float* base = arr == 0 ? p.vcol_grad : (arr == 1 ? p.vpos_grad : p.gnorm);
-    base += (size_t)b * p.N * 3 + comp;
-    float acc = 0.f;
-    unsigned rem = cv;
-    while (rem) {
-      const int l = __ffs(rem) - 1;
-      rem &= rem - 1;
-      if (active) acc += mybuf[l * kVals + lane];
-      if ((endm >> l) & 1u) {
-        const int fr = __shfl_sync(FULL_MASK, face, l);
-        if (active) {
-          const int4 fc = __ldg(p.faces4 + fr);
-          const int vid = vi == 0 ? fc.x : (vi == 1 ? fc.y : fc.z);
-          if (acc != 0.f) atomicAdd(base + (size_t)vid * 3, acc);
-        }
-        acc = 0.f;
+    const int vstride = arr == 2 ? 4 : 3;          // gnorm is float4-strided for aligned gathers in normal_term_kernel
+    base += (size_t)b * p.N * vstride + comp;
+    // one iteration per run [l0, l1] of consecutive pixels that see the same triangle
+    unsigned ends = endm;
+    const float* col = mybuf + (lane < kVals ? lane : 0);
+    while (ends) {
+      const int l1 = __ffs(ends) - 1;
+      ends &= ends - 1;
+      const int l0 = 31 - __clz(head & ((2u << l1) - 1u));
+      float acc = 0.f;
+      for (int l = l0; l <= l1; ++l) acc += col[l * kVals];
+      const int fr = __shfl_sync(FULL_MASK, face, l1);
+      if (active && acc != 0.f) {
+        const int4 fc = __ldg(p.faces4 + fr);
+        const int vid = vi == 0 ? fc.x : (vi == 1 ? fc.y : fc.z);
+        atomicAdd(base + (size_t)vid * vstride, acc);
       }
     }
     __syncwarp();
@@ -353,8 +354,16 @@ pixel_grad_kernel(const PixelParams p) {
     __syncwarp();
     if (lane < kVals) {
       const int ch = lane / 9, k = lane % 9;
-      unsigned rem = cv;
-      while (rem) { const int l = __ffs(rem) - 1; rem &= rem - 1; shsum += mybuf[l * kVals + ch] * mybuf[l * kVals + 3 + k]; }
+      const float* pa = mybuf + ch;
+      const float* py = mybuf + 3 + k;
+      if (cv == FULL_MASK) {
+#pragma unroll
+        for (int l = 0; l < 32; ++l) shsum = fmaf(pa[l * kVals], py[l * kVals], shsum);
+      } else {
+#pragma unroll
+        for (int l = 0; l < 32; ++l)
+          if ((cv >> l) & 1u) shsum = fmaf(pa[l * kVals], py[l * kVals], shsum);
+      }
     }
   }
   if (lane < kVals) shPart[warp][lane] = shsum;
@@ -402,30 +411,32 @@ __global__ void prep_kernel(PrepArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-normal_term_kernel(const float* __restrict__ vertex_pos, const float* __restrict__ gnorm, const int4* __restrict__ faces4,
-                   const int* __restrict__ vfOffsets, const int* __restrict__ vfList, float* __restrict__ vpos_grad, int N) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+// One thread per (batch element, triangle): S = sum of Gn over the triangle's distinct vertices, then
+// the three cross-product Jacobians (getJ_vi/vj/vk, RendererUtil.h:422-539) scattered to its vertices.
+// Triangles none of whose vertices received a normal gradient (about 2/3 of them: back faces,
+// occluded parts) leave after three 16-byte loads.
+__global__ void __launch_bounds__(256)
+normal_term_kernel(const float4* __restrict__ pos4, const float4* __restrict__ gnorm4, const int4* __restrict__ faces4,
+                   float* __restrict__ vpos_grad, int N, int F) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
-  if (n >= N) return;
-  const float* pos = vertex_pos + (size_t)b * N * 3;
-  const float* gn = gnorm + (size_t)b * N * 3;
-  V3 sum = v3(0.f, 0.f, 0.f);
-  const int beg = __ldg(vfOffsets + n), end = __ldg(vfOffsets + n + 1);
-  for (int i = beg; i < end; ++i) {
-    const int4 fc = __ldg(faces4 + __ldg(vfList + i));
-    V3 S = ldv3(gn, fc.x);
-    if (fc.y != fc.x) S = S + ldv3(gn, fc.y);
-    if (fc.z != fc.x && fc.z != fc.y) S = S + ldv3(gn, fc.z);
-    const V3 pi = ldv3(pos, fc.x), pj = ldv3(pos, fc.y), pk = ldv3(pos, fc.z);
-    const V3 e1 = pj - pi, e2 = pk - pi;
-    // S * J_vi = e1 x S - e2 x S ; S * J_vj = e2 x S ; S * J_vk = S x e1   (getJ_vi/vj/vk)
-    if (n == fc.x) sum = sum + (cross(e1, S) - cross(e2, S));
-    if (n == fc.y) sum = sum + cross(e2, S);
-    if (n == fc.z) sum = sum + cross(S, e1);
-  }
-  float* out = vpos_grad + ((size_t)b * N + n) * 3;
-  out[0] += sum.x; out[1] += sum.y; out[2] += sum.z;
+  if (f >= F) return;
+  const int4 fc = __ldg(faces4 + f);
+  const float4* gn = gnorm4 + (size_t)b * N;
+  V3 S = ld4(gn, fc.x);
+  if (fc.y != fc.x) S = S + ld4(gn, fc.y);
+  if (fc.z != fc.x && fc.z != fc.y) S = S + ld4(gn, fc.z);
+  if (S.x == 0.f && S.y == 0.f && S.z == 0.f) return;
+  const float4* pos = pos4 + (size_t)b * N;
+  const V3 pi = ld4(pos, fc.x), pj = ld4(pos, fc.y), pk = ld4(pos, fc.z);
+  const V3 e1 = pj - pi, e2 = pk - pi;
+  // S * J_vi = e1 x S - e2 x S ; S * J_vj = e2 x S ; S * J_vk = S x e1
+  const V3 gj = cross(e2, S), gk = cross(S, e1);
+  const V3 gi = v3(-gj.x - gk.x, -gj.y - gk.y, -gj.z - gk.z);
+  float* out = vpos_grad + (size_t)b * N * 3;
+  atomicAdd(out + 3 * (size_t)fc.x, gi.x); atomicAdd(out + 3 * (size_t)fc.x + 1, gi.y); atomicAdd(out + 3 * (size_t)fc.x + 2, gi.z);
+  atomicAdd(out + 3 * (size_t)fc.y, gj.x); atomicAdd(out + 3 * (size_t)fc.y + 1, gj.y); atomicAdd(out + 3 * (size_t)fc.y + 2, gj.z);
+  atomicAdd(out + 3 * (size_t)fc.z, gk.x); atomicAdd(out + 3 * (size_t)fc.z + 1, gk.y); atomicAdd(out + 3 * (size_t)fc.z + 2, gk.z);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -440,7 +451,7 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const long long nv = (long long)a.B * a.N * 3;
   z.p[0] = a.vpos_grad; z.n[0] = nv;
   z.p[1] = a.vcol_grad; z.n[1] = nv;
-  z.p[2] = a.s.gnorm;   z.n[2] = nv;
+  z.p[2] = a.s.gnorm;   z.n[2] = (long long)a.B * a.N * 4;
   z.p[3] = a.sh_grad;   z.n[3] = (long long)V * 27;
   z.p[4] = a.tex_grad;  z.n[4] = a.tex_grad ? (long long)a.B * a.texH * a.texW * 3 : 0;
   PrepArgs pa;
@@ -466,8 +477,8 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   ++launches;
   if (a.shading == GVV_SHADING_SHADED) {
     tm->begin(K_NORMAL_TERM, st);
-    normal_term_kernel<<<dim3((a.N + 127) / 128, a.B), 128, 0, st>>>(a.vertex_pos, a.s.gnorm, a.faces4, a.vfOffsets, a.vfList,
-                                                                    a.vpos_grad, a.N);
+    normal_term_kernel<<<dim3((a.F + 255) / 256, a.B), 256, 0, st>>>(a.s.bpos4, reinterpret_cast<const float4*>(a.s.gnorm), a.faces4,
+                                                                    a.vpos_grad, a.N, a.F);
     tm->end(st);
     ++launches;
   }

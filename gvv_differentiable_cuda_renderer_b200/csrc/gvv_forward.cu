@@ -270,7 +270,9 @@ static_assert(sizeof(EdgeRec) == 48, "EdgeRec is 48 bytes");
 // Under the pinhole map the 3-D triangle projects exactly onto the 2-D triangle of the projected
 // vertices, and the reference's inside test admits perspective barycentrics >= -0.001, i.e. screen
 // distances up to 0.001 * (zmax/zmin) * height outside an edge.  We keep every pixel centre within
-//     m = 0.25 px + 0.002 * (zmax/zmin) * (longest edge)      (>= 2x that bound + 0.25 px for rounding)
+//     m = margin + 0.002 * (zmax/zmin) * (longest edge)       (2x that bound + `margin` for rounding;
+//                                                              margin = 1/16 px by default, while the fp32
+//                                                              error of the pixel position is ~1e-3 px)
 // of the triangle and send it to the exact test; only pixels farther out are dropped.  Triangles
 // whose projection is unreliable (a vertex at/behind the camera plane, depth ratio > 2, non-finite
 // coordinates) are not culled at all; thin triangles (|area| < 1 px^2, orientation ambiguous) use a

@@ -27,7 +27,7 @@ struct Scratch {
   int* bigCount = nullptr;       // [V]    zeroed by camera_kernel of the next call
   int* bigList = nullptr;        // [V*F]
   int* bins = nullptr;           // [V*F*kMaxSmallTiles]
-  float* gnorm = nullptr;        // [B*N*3] backward: dL/d(unnormalised vertex normal)
+  float* gnorm = nullptr;        // [B*N*4] backward: dL/d(unnormalised vertex normal), float4-strided
   float4* bpos4 = nullptr;       // [B*N]  backward: repacked vertex_pos (raw)
   float4* bcol4 = nullptr;       // [B*N]  backward: repacked vertex_color
   float4* bnor4 = nullptr;       // [V*N]  backward: repacked vertex_normal input
@@ -57,7 +57,7 @@ struct gvv_renderer {
   int F = 0, N = 0, C = 0, W = 0, H = 0;
   int albedo = 0, shading = 0, imgFilter = 1, texFilter = 1, computeNormalMap = 0;
   int tile = 32, tilesX = 0, tilesY = 0, nT = 0;
-  float cullMargin = 0.25f;   // px; < 0 disables the conservative screen-space pre-test
+  float cullMargin = 0.0625f; // px (fixed part of the margin); < 0 disables the conservative screen-space pre-test
   bool hasTexcoords = false;
   int4* faces4 = nullptr;     // [F] (v0,v1,v2,0)
   float* texcoords = nullptr; // [F*6]

@@ -136,7 +136,7 @@ int gvv_debug_eval(gvv_handle h, int32_t n, const int32_t* queries, int32_t* out
 
 /* Runtime knobs: key "tile" (16|32 rasteriser tile edge; default 32); key "cull_margin_milli" (fixed
  * part, in 1/1000 pixel, of the margin of the conservative screen-space pre-test that decides which
- * bbox pixels get the exact test; default 250; negative = test every bbox pixel exactly, like the
+ * bbox pixels get the exact test; default 62 (1/16 px); negative = test every bbox pixel exactly, like the
  * reference -- results are identical either way, see tests); key "time_kernels" (1: record
  * a CUDA-event pair around every kernel on the launching stream, 0: off; either resets the log).
  * Returns 0 on success. */
