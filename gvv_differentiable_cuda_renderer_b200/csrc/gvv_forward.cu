@@ -261,9 +261,10 @@ static_assert(sizeof(TriRec) == 80, "TriRec is 80 bytes");
 struct __align__(16) EdgeRec {
   float A0, B0, C0, A1;
   float B1, C1, A2, B2;
-  float C2; int start; int geom; int rcpw;   // geom = x0 | y0 << 8 | w << 16 (tile-local)
-};
-static_assert(sizeof(EdgeRec) == 48, "EdgeRec is 48 bytes");
+  float C2, R0, R1, R2;                      // R_i = -1/A_i (0 when the edge is treated as horizontal)
+  int start; int geom; int pad0; int pad1;   // start = first ROW of this triangle in the chunk's row list;
+};                                           // geom = x0 | y0 << 8 | w << 16 (tile-local)
+static_assert(sizeof(EdgeRec) == 64, "EdgeRec is 64 bytes");
 
 // Conservative screen-space reject.  The reference tests EVERY pixel of the bbox with the exact
 // 3-D test; a pair that fails it has no effect at all, so pairs that provably fail may be skipped.
@@ -277,10 +278,32 @@ static_assert(sizeof(EdgeRec) == 48, "EdgeRec is 48 bytes");
 // whose projection is unreliable (a vertex at/behind the camera plane, depth ratio > 2, non-finite
 // coordinates) are not culled at all; thin triangles (|area| < 1 px^2, orientation ambiguous) use a
 // two-sided band around their longest edge.  e_i(lx,ly) = A_i*lx + B_i*ly + C_i >= 0 keeps the pixel.
+// Row form of the pre-test: on row ly, e_i >= 0 <=> x >= t_i (A_i > 0) or x <= t_i (A_i < 0) with
+// t_i = (B_i*ly + C_i) * R_i, R_i = -1/A_i.  An edge with |A_i| * 32 below 1e-4 of its own slack is
+// treated as horizontal (A_i := 0, its 32*|A_i| variation across the tile is added to C_i).
+__device__ __forceinline__ void edge_finish(EdgeRec& e) {
+  float* A[3] = {&e.A0, &e.A1, &e.A2};
+  float* B[3] = {&e.B0, &e.B1, &e.B2};
+  float* C[3] = {&e.C0, &e.C1, &e.C2};
+  float* R[3] = {&e.R0, &e.R1, &e.R2};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float a = *A[i];
+    if (fabsf(a) * 64.f <= 1.0e-3f * fabsf(*B[i]) || a == 0.f) {
+      *C[i] += 64.f * fabsf(a);
+      *A[i] = 0.f;
+      *R[i] = 0.f;
+    } else {
+      *R[i] = -1.f / a;
+    }
+  }
+}
+
 __device__ __forceinline__ void edge_setup(float4 p0, float4 p1, float4 p2, float ox, float oy, float margin, EdgeRec& e) {
   const float x0 = p0.x - ox, y0 = p0.y - oy, x1 = p1.x - ox, y1 = p1.y - oy, x2 = p2.x - ox, y2 = p2.y - oy;
   const float zmin = fminf(p0.z, fminf(p1.z, p2.z)), zmax = fmaxf(p0.z, fmaxf(p1.z, p2.z));
   e.A0 = e.B0 = e.A1 = e.B1 = e.A2 = e.B2 = 0.f;
+  e.R0 = e.R1 = e.R2 = 0.f;
   e.C0 = e.C1 = e.C2 = 1.f;                                   // default: keep everything
   if (!(margin >= 0.f) || !(zmin > 1.0e-4f) || !(zmax <= 2.f * zmin)) return;   // margin < 0: culling off
   const float ax = x1 - x0, ay = y1 - y0, bx = x2 - x1, by = y2 - y1, cx = x0 - x2, cy = y0 - y2;
@@ -304,6 +327,7 @@ __device__ __forceinline__ void edge_setup(float4 p0, float4 p1, float4 p2, floa
     e.A0 = A; e.B0 = B; e.C0 = C + T;
     e.A1 = -A; e.B1 = -B; e.C1 = -C + T;
   }
+  edge_finish(e);
 }
 
 struct RasterParams {
@@ -347,13 +371,14 @@ raster_kernel(const RasterParams p) {
   constexpr int NPIX = TS * TS;
   constexpr int CHUNK = 128;
   constexpr int SHIFT = 21;
-  constexpr int QCAP = 64;            // per-warp survivor ring (power of two, >= 2*32)
+  constexpr int QCAP = 64;            // per-warp span list: 32 spans + 32 sentinels
   __shared__ unsigned long long zt[NPIX];
   __shared__ float rayx[NPIX], rayy[NPIX], rayz[NPIX];
   __shared__ TriRec rec[CHUNK];
   __shared__ EdgeRec erec[CHUNK];
   __shared__ int startArr[CHUNK + 40];
-  __shared__ int queue[8][QCAP];
+  __shared__ int spanStart[8][QCAP + 4];
+  __shared__ int spanInfo[8][32];
   __shared__ int warpTot[8];
   __shared__ float shc[27];
   __shared__ CamRec cam;
@@ -396,32 +421,29 @@ raster_kernel(const RasterParams p) {
     rayx[q] = rd.x; rayy[q] = rd.y; rayz[q] = rd.z;
   }
 
-  // exact test + 64-bit atomicMin for up to 32 queued (triangle, pixel) pairs
-  int* myq = queue[warp];
-  auto drain = [&](int head, int n) {
-    if (lane < n) {
-      const int ent = myq[(head + lane) & (QCAP - 1)];
-      const int k = ent >> 10, q = ent & 1023;
-      const float4* rp = reinterpret_cast<const float4*>(&rec[k]);
-      const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3];
-      const int4 r4 = reinterpret_cast<const int4*>(rp)[4];
-      TriSetup ts;
-      ts.v0 = mk3(r0.x, r0.y, r0.z); ts.v1 = mk3(r0.w, r1.x, r1.y); ts.v2 = mk3(r1.z, r1.w, r2.x);
-      ts.N = mk3(r2.y, r2.z, r2.w); ts.num = r3.x; ts.den = r3.y;
-      const F3 rd = mk3(rayx[q], rayy[q], rayz[q]);
-      float a, bq, c;
-      if (hit_exact(ts, ros, rd, a, bq, c)) {
-        const int depth = depth_key_exact(a, bq, c, r3.z, r3.w, __int_as_float(r4.x));
-        const unsigned long long key = pack_key(depth, r4.y);
-        unsigned long long cur = zt[q];
-        while (key < cur) {                     // 64-bit atomicMin on the shared z-tile
-          const unsigned long long old = atomicCAS(&zt[q], cur, key);
-          if (old == cur) break;
-          cur = old;
-        }
+  // exact test + 64-bit atomicMin for one (triangle k of the chunk, tile pixel q) pair
+  auto exact_pair = [&](int k, int q) {
+    const float4* rp = reinterpret_cast<const float4*>(&rec[k]);
+    const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3];
+    const int4 r4 = reinterpret_cast<const int4*>(rp)[4];
+    TriSetup ts;
+    ts.v0 = mk3(r0.x, r0.y, r0.z); ts.v1 = mk3(r0.w, r1.x, r1.y); ts.v2 = mk3(r1.z, r1.w, r2.x);
+    ts.N = mk3(r2.y, r2.z, r2.w); ts.num = r3.x; ts.den = r3.y;
+    const F3 rd = mk3(rayx[q], rayy[q], rayz[q]);
+    float a, bq, c;
+    if (hit_exact(ts, ros, rd, a, bq, c)) {
+      const int depth = depth_key_exact(a, bq, c, r3.z, r3.w, __int_as_float(r4.x));
+      const unsigned long long key = pack_key(depth, r4.y);
+      unsigned long long cur = zt[q];
+      while (key < cur) {                     // 64-bit atomicMin on the shared z-tile
+        const unsigned long long old = atomicCAS(&zt[q], cur, key);
+        if (old == cur) break;
+        cur = old;
       }
     }
   };
+  int* mySpanStart = spanStart[warp];
+  int* mySpanInfo = spanInfo[warp];
 
   // ---- rasterise: the tile's own bin, then the view's big-triangle list ----
   for (int pass = 0; pass < 2; ++pass) {
@@ -446,7 +468,7 @@ raster_kernel(const RasterParams p) {
         const int cy0 = max(bb.y, tileY0), cy1 = min(bb.w, tileY0 + TS - 1);
         const int w = cx1 - cx0 + 1, h = cy1 - cy0 + 1;
         if (w > 0 && h > 0) {
-          n = w * h;
+          n = h;                 // work items are ROWS of the clipped bbox
           const TriSetup ts = tri_setup_exact(mk3(s0.x, s0.y, s0.z), mk3(s1.x, s1.y, s1.z), mk3(s2.x, s2.y, s2.z), ros);
           mine.v0x = ts.v0.x; mine.v0y = ts.v0.y; mine.v0z = ts.v0.z;
           mine.v1x = ts.v1.x; mine.v1y = ts.v1.y; mine.v1z = ts.v1.z;
@@ -456,7 +478,7 @@ raster_kernel(const RasterParams p) {
           mine.face = f; mine.pad0 = 0; mine.pad1 = 0;
           edge_setup(p0, p1, p2, (float)tileX0, (float)tileY0, p.cullMargin, em);
           em.geom = (cx0 - tileX0) | ((cy0 - tileY0) << 8) | (w << 16);
-          em.rcpw = ((1 << 18) + w - 1) / w;
+          em.pad0 = 0; em.pad1 = 0;
         }
       }
       // block-wide exclusive scan of (1 << SHIFT | n): rank among non-empty triangles + first fragment
@@ -482,50 +504,72 @@ raster_kernel(const RasterParams p) {
       __syncthreads();
       if (nfrag == 0) continue;
 
-      // fragments [0, nfrag) are split evenly over the 8 warps (32-aligned), whatever the triangle sizes
+      // rows [0, nfrag) are split evenly over the 8 warps (32-aligned), whatever the triangle sizes
       const int per = ((nfrag + 7) / 8 + 31) & ~31;
       const int lo = warp * per, hi = min(lo + per, nfrag);
       if (lo < hi) {
         int c0 = 0;
         for (int j = lane; j < ntri; j += 32) c0 += (startArr[j] <= lo) ? 1 : 0;
-        int K0 = __reduce_add_sync(FULL_MASK, c0) - 1;   // triangle containing fragment `lo`
-        int qhead = 0, qcount = 0;
+        int K0 = __reduce_add_sync(FULL_MASK, c0) - 1;   // triangle owning row `lo`
         for (int fb = lo; fb < hi; fb += 32) {
+          // (1) one bbox row per lane: which triangle, which row
           const int s = startArr[K0 + 1 + lane];
           const unsigned bits = (s < fb + 32) ? (1u << (s - fb)) : 0u;
           const unsigned mask = __reduce_or_sync(FULL_MASK, bits);
           const int k = K0 + __popc(mask & ((2u << lane) - 1u));
           K0 += __popc(mask);
           const int fr = fb + lane;
-          bool keep = false;
-          int ent = 0;
+          // (2) conservative x-span of the row: pixels outside it provably fail the exact test
+          int cnt = 0, info = 0;
           if (fr < hi) {
             const float4* ep = reinterpret_cast<const float4*>(&erec[k]);
-            const float4 e0 = ep[0], e1 = ep[1];
-            const int4 e2 = reinterpret_cast<const int4*>(ep)[2];
-            const int local = fr - e2.y;
-            const int w = e2.z >> 16;
-            const int dy = (int)(((unsigned)local * (unsigned)e2.w) >> 18);
-            const int lx = (e2.z & 0xff) + local - dy * w, ly = ((e2.z >> 8) & 0xff) + dy;
-            const float fx = (float)lx, fy = (float)ly;
-            const float t0 = fmaf(e0.x, fx, fmaf(e0.y, fy, e0.z));
-            const float t1 = fmaf(e0.w, fx, fmaf(e1.x, fy, e1.y));
-            const float t2 = fmaf(e1.z, fx, fmaf(e1.w, fy, __int_as_float(e2.x)));
-            keep = fminf(t0, fminf(t1, t2)) >= 0.f;
-            ent = (k << 10) | (ly * TS + lx);
+            const float4 e0 = ep[0], e1 = ep[1], e2 = ep[2];
+            const int4 e3 = reinterpret_cast<const int4*>(ep)[3];
+            const int x0 = e3.y & 0xff, ly = ((e3.y >> 8) & 0xff) + (fr - e3.x), w = e3.y >> 16;
+            const float fy = (float)ly;
+            const float s0 = fmaf(e0.y, fy, e0.z), s1 = fmaf(e1.x, fy, e1.y), s2 = fmaf(e1.w, fy, e2.x);
+            // A_i > 0: x >= t_i ; A_i < 0: x <= t_i ; A_i == 0: row kept iff s_i >= 0
+            float xlo = -1.0e30f, xhi = 1.0e30f;
+            bool ok = true;
+            { const float t = s0 * e2.y; if (e0.x > 0.f) xlo = fmaxf(xlo, t); else if (e0.x < 0.f) xhi = fminf(xhi, t); else ok = ok && (s0 >= 0.f); }
+            { const float t = s1 * e2.z; if (e0.w > 0.f) xlo = fmaxf(xlo, t); else if (e0.w < 0.f) xhi = fminf(xhi, t); else ok = ok && (s1 >= 0.f); }
+            { const float t = s2 * e2.w; if (e1.z > 0.f) xlo = fmaxf(xlo, t); else if (e1.z < 0.f) xhi = fminf(xhi, t); else ok = ok && (s2 >= 0.f); }
+            // 1e-3 px of slack for the rounding of t_i (|t| <= ~64 wherever it matters), then clamp to the bbox row
+            const int xl = max(x0, (int)ceilf(fmaxf(xlo - 1.0e-3f, -1.0f)));
+            const int xr = min(x0 + w - 1, (int)floorf(fminf(xhi + 1.0e-3f, 64.0f)));
+            cnt = ok ? max(0, xr - xl + 1) : 0;
+            info = (k << 10) | (ly << 5) | xl;
           }
-          const unsigned km = __ballot_sync(FULL_MASK, keep);
-          if (keep) myq[(qhead + qcount + __popc(km & ((1u << lane) - 1u))) & (QCAP - 1)] = ent;
-          qcount += __popc(km);
+          // (3) compact the non-empty spans of these 32 rows, (4) expand them 32 pixels at a time
+          int incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += y; }
+          const int total = __shfl_sync(FULL_MASK, incl, 31);
+          const unsigned nz = __ballot_sync(FULL_MASK, cnt > 0);
+          const int nspan = __popc(nz);
+          if (cnt > 0) {
+            const int r = __popc(nz & ((1u << lane) - 1u));
+            mySpanStart[r] = incl - cnt;
+            mySpanInfo[r] = info;
+          }
+          mySpanStart[nspan + lane] = 0x7fffffff;
+          if (lane == 0) mySpanStart[nspan + 32] = 0x7fffffff;
           __syncwarp();
-          if (qcount >= 32) {
-            drain(qhead, 32);
-            qhead = (qhead + 32) & (QCAP - 1);
-            qcount -= 32;
-            __syncwarp();
+          int S0 = 0;
+          for (int t0 = 0; t0 < total; t0 += 32) {
+            const int ss = mySpanStart[S0 + 1 + lane];
+            const unsigned sb = (ss < t0 + 32) ? (1u << (ss - t0)) : 0u;
+            const unsigned sm = __reduce_or_sync(FULL_MASK, sb);
+            const int si = S0 + __popc(sm & ((2u << lane) - 1u));
+            S0 += __popc(sm);
+            const int t = t0 + lane;
+            if (t < total) {
+              const int inf = mySpanInfo[si];
+              exact_pair(inf >> 10, ((inf >> 5) & 31) * TS + (inf & 31) + (t - mySpanStart[si]));
+            }
           }
+          __syncwarp();
         }
-        if (qcount > 0) { drain(qhead, qcount); __syncwarp(); }
       }
     }
   }
