@@ -38,7 +38,7 @@ static cudaError_t dmalloc(T** p, size_t count) {
 }
 
 static void free_scratch(Scratch& s) {
-  cudaFree(s.cams); cudaFree(s.proj); cudaFree(s.vscaled); cudaFree(s.vnorm4); cudaFree(s.vcol4);
+  cudaFree(s.cams); cudaFree(s.proj); cudaFree(s.vscaled); cudaFree(s.fnorm4); cudaFree(s.vnorm4); cudaFree(s.vcol4);
   cudaFree(s.tileCount); cudaFree(s.tileCursor); cudaFree(s.tileOffset); cudaFree(s.tileOrder); cudaFree(s.bigCount);
   cudaFree(s.bigList); cudaFree(s.bins); cudaFree(s.gnorm); cudaFree(s.bpos4); cudaFree(s.bcol4); cudaFree(s.bnor4);
   s = Scratch();
@@ -64,6 +64,7 @@ static int ensure_scratch(gvv_renderer* h, int B, cudaStream_t st) {
   acc(dmalloc(&s.cams, (size_t)V));
   acc(dmalloc(&s.proj, (size_t)V * N));
   acc(dmalloc(&s.vscaled, (size_t)B * N));
+  acc(dmalloc(&s.fnorm4, (size_t)B * F));
   acc(dmalloc(&s.vnorm4, (size_t)B * N));
   acc(dmalloc(&s.vcol4, (size_t)B * N));
   acc(dmalloc(&s.tileCount, (size_t)V * nT));

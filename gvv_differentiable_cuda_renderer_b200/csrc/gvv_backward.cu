@@ -102,6 +102,7 @@ struct PixelParams {
 };
 
 constexpr int kVals = 27;
+constexpr int kRow = 36;    // 32 pixels + 4 pad: a quarter-warp's float4 reads of 8 different rows hit 32 different banks
 
 // Tolerance-level arithmetic of the backward: reciprocal-multiply instead of IEEE divides
 // (gradients are compared to rel-L2 1e-4; the visibility-critical ray uses the exact functions).
@@ -142,7 +143,7 @@ __device__ __forceinline__ V3 ld4(const float4* __restrict__ p, size_t i) { cons
 // grid (W/32, H/8, V), 256 threads: warp w owns the 32-pixel scanline segment y = 8*by + w.
 __global__ void __launch_bounds__(256, 3)
 pixel_grad_kernel(const PixelParams p) {
-  __shared__ float buf[8][32 * kVals];
+  __shared__ __align__(16) float buf[8][kVals * kRow];   // per warp: value-major, kRow floats per value (32 pixels + pad)
   __shared__ float shPart[8][kVals];
   __shared__ CamRec cam;
   __shared__ float shc[27];
@@ -162,7 +163,7 @@ pixel_grad_kernel(const PixelParams p) {
   __syncthreads();
 
   float* mybuf = buf[warp];
-  float* mine = mybuf + lane * kVals;
+  float* mine = mybuf + lane;   // value j of this lane's pixel lives at mine[j * kRow]
   const unsigned cv = __ballot_sync(FULL_MASK, covered);
   float gA[3] = {0.f, 0.f, 0.f};
   float Y[9];
@@ -212,7 +213,7 @@ pixel_grad_kernel(const PixelParams p) {
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int ch = 0; ch < 3; ++ch) mine[i * 3 + ch] = gl[ch] * bc[i];
+          for (int ch = 0; ch < 3; ++ch) mine[(i * 3 + ch) * kRow] = gl[ch] * bc[i];
       } else if (p.albedo == GVV_ALBEDO_TEXTURED) {
         const float* tc = p.texcoords + (size_t)face * 6;
         float u = (__ldg(tc + 0) * bc[0] + __ldg(tc + 2) * bc[1] + __ldg(tc + 4) * bc[2]) * p.texW;
@@ -263,7 +264,7 @@ pixel_grad_kernel(const PixelParams p) {
         pos9[6] = g2.x; pos9[7] = g2.y; pos9[8] = g2.z;
         // vertex-normal gradient, finished in normal_term_kernel
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { mine[18 + i * 3] = bc[i] * q.x; mine[19 + i * 3] = bc[i] * q.y; mine[20 + i * 3] = bc[i] * q.z; }
+        for (int i = 0; i < 3; ++i) { mine[(18 + i * 3) * kRow] = bc[i] * q.x; mine[(19 + i * 3) * kRow] = bc[i] * q.y; mine[(20 + i * 3) * kRow] = bc[i] * q.z; }
       }
 
       // ---- model-to-data term (:531-555) ----
@@ -309,7 +310,7 @@ pixel_grad_kernel(const PixelParams p) {
         }
       }
 #pragma unroll
-      for (int j = 0; j < 9; ++j) mine[9 + j] = pos9[j];
+      for (int j = 0; j < 9; ++j) mine[(9 + j) * kRow] = pos9[j];
     }
 
     // ---- run-aggregated scatter: lane j owns value j ----
@@ -324,45 +325,48 @@ pixel_grad_kernel(const PixelParams p) {
     float* base = arr == 0 ? p.vcol_grad : (arr == 1 ? p.vpos_grad : p.gnorm);
     const int vstride = arr == 2 ? 4 : 3;          // gnorm is float4-strided for aligned gathers in normal_term_kernel
     base += (size_t)b * p.N * vstride + comp;
-    // one iteration per run [l0, l1] of consecutive pixels that see the same triangle
-    unsigned ends = endm;
-    const float* col = mybuf + (lane < kVals ? lane : 0);
-    while (ends) {
-      const int l1 = __ffs(ends) - 1;
-      ends &= ends - 1;
-      const int l0 = 31 - __clz(head & ((2u << l1) - 1u));
-      float acc = 0.f;
-      for (int l = l0; l <= l1; ++l) acc += col[l * kVals];
-      const int fr = __shfl_sync(FULL_MASK, face, l1);
-      if (active && acc != 0.f) {
-        const int4 fc = __ldg(p.faces4 + fr);
-        const int vid = vi == 0 ? fc.x : (vi == 1 ? fc.y : fc.z);
-        atomicAdd(base + (size_t)vid * vstride, acc);
+    // Lane j walks row j (the 32 pixels' value j) with a segmented running sum: reset at the head
+    // of every run of equal face id, flushed with ONE warp-wide atomic at its end.  head/endm are
+    // warp-uniform, so the 32 steps are unrolled with uniform branches; pixels outside a run may hold
+    // stale data -- it is discarded by the reset at the next head.
+    const float4* row = reinterpret_cast<const float4*>(mybuf + (lane < kVals ? lane : 0) * kRow);
+    float acc = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 v4 = row[g];
+      const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int l = 4 * g + u;
+        acc = ((head >> l) & 1u) ? vv[u] : acc + vv[u];
+        if ((endm >> l) & 1u) {
+          const int fr = __shfl_sync(FULL_MASK, face, l);
+          if (active && acc != 0.f) {
+            const int4 fc = __ldg(p.faces4 + fr);
+            const int vid = vi == 0 ? fc.x : (vi == 1 ? fc.y : fc.z);
+            atomicAdd(base + (size_t)vid * vstride, acc);
+          }
+        }
       }
     }
     __syncwarp();
   }
 
-  // ---- SH gradient: 12 values per pixel (g*albedo, Y), lane j = (ch,k) sums gA[ch]*Y[k]; warp -> block -> 27 atomics ----
+  // ---- SH gradient: 12 values per pixel (g*albedo, Y) stored value-major; lane j = (ch,k) sums
+  // gA[ch]*Y[k] over the 32 pixels with float4 reads (uncovered pixels store zeros); warp -> block -> 27 atomics ----
   float shsum = 0.f;
   if (shaded && cv) {
-    if (covered) {
-      mine[0] = gA[0]; mine[1] = gA[1]; mine[2] = gA[2];
+    mine[0 * kRow] = gA[0]; mine[1 * kRow] = gA[1]; mine[2 * kRow] = gA[2];   // zeros where not covered
 #pragma unroll
-      for (int k = 0; k < 9; ++k) mine[3 + k] = Y[k];
-    }
+    for (int k = 0; k < 9; ++k) mine[(3 + k) * kRow] = Y[k];
     __syncwarp();
     if (lane < kVals) {
-      const int ch = lane / 9, k = lane % 9;
-      const float* pa = mybuf + ch;
-      const float* py = mybuf + 3 + k;
-      if (cv == FULL_MASK) {
+      const float4* pa = reinterpret_cast<const float4*>(mybuf + (lane / 9) * kRow);
+      const float4* py = reinterpret_cast<const float4*>(mybuf + (3 + lane % 9) * kRow);
 #pragma unroll
-        for (int l = 0; l < 32; ++l) shsum = fmaf(pa[l * kVals], py[l * kVals], shsum);
-      } else {
-#pragma unroll
-        for (int l = 0; l < 32; ++l)
-          if ((cv >> l) & 1u) shsum = fmaf(pa[l * kVals], py[l * kVals], shsum);
+      for (int g = 0; g < 8; ++g) {
+        const float4 a4 = pa[g], y4 = py[g];
+        shsum = fmaf(a4.x, y4.x, fmaf(a4.y, y4.y, fmaf(a4.z, y4.z, fmaf(a4.w, y4.w, shsum))));
       }
     }
   }

@@ -1,9 +1,10 @@
 // gvv_forward.cu -- forward pass of the rasteriser for sm_100a.
 //
 // Replaces the reference's eight per-batch-element launches (CUDABasedRasterization.cu:449-473)
-// by six launches that cover ALL batch elements and cameras at once:
+// by seven launches that cover ALL batch elements and cameras at once:
 //
 //   camera_kernel     per view        E^-1, (K*E)^-1, ray origin            (ref :23-67)
+//   face_normal_kernel per (b, tri)   cross(v1-v0, v2-v0), once per batch element  (ref :122-141)
 //   vertex_kernel     per (b, vertex) /1000 pre-scale, vertex normal via CSR, projection into
 //                                     every camera of b, colour repack       (ref :98-174)
 //   bin_count_kernel  per (view, tri) bbox (ref :184-208) -> tile histogram / big list
@@ -58,12 +59,25 @@ __device__ __forceinline__ F3 ld3(const float* __restrict__ p, int i) {
   return mk3(__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2));
 }
 
+// face normals cross(v1-v0, v2-v0), world space, once per batch element (ref :122-141 computes them C times)
+__global__ void __launch_bounds__(256)
+face_normal_kernel(const float* __restrict__ vertex_pos, const int4* __restrict__ faces4, float4* __restrict__ fnorm4, int N, int F) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (f >= F) return;
+  const float* pos = vertex_pos + (size_t)b * N * 3;
+  const int4 fc = __ldg(faces4 + f);
+  const F3 a = ld3(pos, fc.x), bb = ld3(pos, fc.y), cc = ld3(pos, fc.z);
+  const F3 fn = cross3x(sub3(bb, a), sub3(cc, a));
+  fnorm4[(size_t)b * F + f] = make_float4(fn.x, fn.y, fn.z, 0.f);
+}
+
 __global__ void __launch_bounds__(128)
 vertex_kernel(const float* __restrict__ vertex_pos, const float* __restrict__ vertex_color,
-              const int4* __restrict__ faces4, const int* __restrict__ vfOffsets, const int* __restrict__ vfList,
+              const float4* __restrict__ fnorm4, const int* __restrict__ vfOffsets, const int* __restrict__ vfList,
               const CamRec* __restrict__ cams, float4* __restrict__ proj, float4* __restrict__ vscaled,
               float4* __restrict__ vnorm4, float4* __restrict__ vcol4, float* __restrict__ vertex_normal_out,
-              int N, int C) {
+              int N, int F, int C) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (n >= N) return;
@@ -74,15 +88,14 @@ vertex_kernel(const float* __restrict__ vertex_pos, const float* __restrict__ ve
     const F3 col = ld3(vertex_color + (size_t)b * N * 3, n);
     vcol4[(size_t)b * N + n] = make_float4(col.x, col.y, col.z, 0.f);
   }
-  // vertex normal = sum of incident face normals in ascending face order (ref :122-174); the
+  // vertex normal = sum of incident face normals in ascending face order (ref :148-174); the
   // reference leaves vertices without faces uninitialised, we define them as 0.
   F3 nrm = mk3(0.f, 0.f, 0.f);
   const int beg = __ldg(vfOffsets + n), end = __ldg(vfOffsets + n + 1);
+  const float4* fnb = fnorm4 + (size_t)b * F;
   for (int i = beg; i < end; ++i) {
-    const int4 fc = __ldg(faces4 + __ldg(vfList + i));
-    const F3 a = ld3(pos, fc.x), bb = ld3(pos, fc.y), cc = ld3(pos, fc.z);
-    const F3 fn = cross3x(sub3(bb, a), sub3(cc, a));
-    if (i == beg) nrm = fn;
+    const float4 fn = __ldg(fnb + __ldg(vfList + i));
+    if (i == beg) nrm = mk3(fn.x, fn.y, fn.z);
     else nrm = mk3(__fadd_rn(nrm.x, fn.x), __fadd_rn(nrm.y, fn.y), __fadd_rn(nrm.z, fn.z));
   }
   vnorm4[(size_t)b * N + n] = make_float4(nrm.x, nrm.y, nrm.z, 0.f);
@@ -365,23 +378,24 @@ __device__ __forceinline__ float sh_eval(const float* __restrict__ sh, F3 n) {
   return s;
 }
 
+// Shared-memory plan of raster_kernel (dynamic, carved by hand):
+//   zt[TS*TS] u64 | rayx,rayy,rayz[TS*TS] f32 | per warp: rec[32], erec[32], startArr[68], spanStart[68], spanInfo[32]
+constexpr int kWarpSmemBytes = 32 * (int)sizeof(TriRec) + 32 * (int)sizeof(EdgeRec) + (68 + 68 + 32) * 4;
+template <int TS>
+constexpr int raster_smem_bytes() { return TS * TS * (8 + 12) + 8 * kWarpSmemBytes; }
+
 template <int TS>
 __global__ void __launch_bounds__(256, 3)
 raster_kernel(const RasterParams p) {
   constexpr int NPIX = TS * TS;
-  constexpr int CHUNK = 128;
-  constexpr int SHIFT = 21;
-  constexpr int QCAP = 64;            // per-warp span list: 32 spans + 32 sentinels
-  __shared__ unsigned long long zt[NPIX];
-  __shared__ float rayx[NPIX], rayy[NPIX], rayz[NPIX];
-  __shared__ TriRec rec[CHUNK];
-  __shared__ EdgeRec erec[CHUNK];
-  __shared__ int startArr[CHUNK + 40];
-  __shared__ int spanStart[8][QCAP + 4];
-  __shared__ int spanInfo[8][32];
-  __shared__ int warpTot[8];
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  unsigned long long* zt = reinterpret_cast<unsigned long long*>(smemRaw);
+  float* rayx = reinterpret_cast<float*>(smemRaw + NPIX * 8);
+  float* rayy = rayx + NPIX;
+  float* rayz = rayy + NPIX;
   __shared__ float shc[27];
   __shared__ CamRec cam;
+  __shared__ int nextBatch;
 
   // 1-D grid, view fastest: the heaviest tiles of every view are scheduled first
   const int view = blockIdx.x % p.V;
@@ -410,6 +424,7 @@ raster_kernel(const RasterParams p) {
 
   if (tid < 64) reinterpret_cast<float*>(&cam)[tid] = reinterpret_cast<const float*>(p.cams + view)[tid];
   if (tid >= 64 && tid < 64 + 27) shc[tid - 64] = p.sh_coeff[(size_t)view * 27 + (tid - 64)];
+  if (tid == 128) nextBatch = 0;
   __syncthreads();
   const F3 ros = mk3(cam.ros[0], cam.ros[1], cam.ros[2]);
 
@@ -420,8 +435,19 @@ raster_kernel(const RasterParams p) {
     const F3 rd = ray_dir_exact(cam.Pinv, cam.ro, __fadd_rn((float)x, 0.5f), __fadd_rn((float)y, 0.5f));
     rayx[q] = rd.x; rayy[q] = rd.y; rayz[q] = rd.z;
   }
+  __syncthreads();
 
-  // exact test + 64-bit atomicMin for one (triangle k of the chunk, tile pixel q) pair
+  // ---- rasterise.  Every warp works on its own: it grabs a batch of up to 32 triangles of the
+  // tile's bin (then of the view's big-triangle list), sets them up into its private records, and
+  // rasterises them; no block-wide barrier until all batches are done. ----
+  unsigned char* wbase = smemRaw + NPIX * 20 + warp * kWarpSmemBytes;
+  TriRec* rec = reinterpret_cast<TriRec*>(wbase);
+  EdgeRec* erec = reinterpret_cast<EdgeRec*>(wbase + 32 * sizeof(TriRec));
+  int* startArr = reinterpret_cast<int*>(wbase + 32 * (sizeof(TriRec) + sizeof(EdgeRec)));
+  int* mySpanStart = startArr + 68;
+  int* mySpanInfo = mySpanStart + 68;
+
+  // exact test + 64-bit atomicMin for one (triangle k of the batch, tile pixel q) pair
   auto exact_pair = [&](int k, int q) {
     const float4* rp = reinterpret_cast<const float4*>(&rec[k]);
     const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3];
@@ -442,135 +468,121 @@ raster_kernel(const RasterParams p) {
       }
     }
   };
-  int* mySpanStart = spanStart[warp];
-  int* mySpanInfo = spanInfo[warp];
 
-  // ---- rasterise: the tile's own bin, then the view's big-triangle list ----
-  for (int pass = 0; pass < 2; ++pass) {
-    const int cnt = pass == 0 ? cntSmall : cntBig;
-    const int* list = pass == 0 ? p.bins + (size_t)view * p.F * kMaxSmallTiles + p.tileOffset[tidx]
-                                : p.bigList + (size_t)view * p.F;
-    for (int chunk = 0; chunk < cnt; chunk += CHUNK) {
-      __syncthreads();   // rec/erec/startArr of the previous chunk (and the z-tile clear) are done
-      const int i = chunk + tid;
-      int n = 0;
-      TriRec mine;
-      EdgeRec em;
-      if (tid < CHUNK && i < cnt) {
-        const int f = __ldg(list + i);
-        const int4 fc = __ldg(p.faces4 + f);
-        const float4* vs = p.vscaled + (size_t)b * p.N;
-        const float4* pj = p.proj + (size_t)view * p.N;
-        const float4 s0 = __ldg(vs + fc.x), s1 = __ldg(vs + fc.y), s2 = __ldg(vs + fc.z);
-        const float4 p0 = __ldg(pj + fc.x), p1 = __ldg(pj + fc.y), p2 = __ldg(pj + fc.z);
-        const int4 bb = bbox_exact(p0, p1, p2, p.W, p.H);
-        const int cx0 = max(bb.x, tileX0), cx1 = min(bb.z, tileX0 + TS - 1);
-        const int cy0 = max(bb.y, tileY0), cy1 = min(bb.w, tileY0 + TS - 1);
-        const int w = cx1 - cx0 + 1, h = cy1 - cy0 + 1;
-        if (w > 0 && h > 0) {
-          n = h;                 // work items are ROWS of the clipped bbox
-          const TriSetup ts = tri_setup_exact(mk3(s0.x, s0.y, s0.z), mk3(s1.x, s1.y, s1.z), mk3(s2.x, s2.y, s2.z), ros);
-          mine.v0x = ts.v0.x; mine.v0y = ts.v0.y; mine.v0z = ts.v0.z;
-          mine.v1x = ts.v1.x; mine.v1y = ts.v1.y; mine.v1z = ts.v1.z;
-          mine.v2x = ts.v2.x; mine.v2y = ts.v2.y; mine.v2z = ts.v2.z;
-          mine.Nx = ts.N.x; mine.Ny = ts.N.y; mine.Nz = ts.N.z;
-          mine.num = ts.num; mine.den = ts.den; mine.z0 = p0.z; mine.z1 = p1.z; mine.z2 = p2.z;
-          mine.face = f; mine.pad0 = 0; mine.pad1 = 0;
-          edge_setup(p0, p1, p2, (float)tileX0, (float)tileY0, p.cullMargin, em);
-          em.geom = (cx0 - tileX0) | ((cy0 - tileY0) << 8) | (w << 16);
-          em.pad0 = 0; em.pad1 = 0;
+  const int cntAll = cntSmall + cntBig;
+  const int G = min(32, max(1, (cntAll + 7) / 8));      // triangles per batch: few big ones are spread over the warps
+  const int* smallList = p.bins + (size_t)view * p.F * kMaxSmallTiles + p.tileOffset[tidx];
+  const int* bigList = p.bigList + (size_t)view * p.F;
+  const float4* vs = p.vscaled + (size_t)b * p.N;
+  const float4* pj = p.proj + (size_t)view * p.N;
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&nextBatch, G);
+    base = __shfl_sync(FULL_MASK, base, 0);
+    if (base >= cntAll) break;
+    const int i = base + lane;
+    int n = 0;
+    TriRec mine;
+    EdgeRec em;
+    if (lane < G && i < cntAll) {
+      const int f = __ldg(i < cntSmall ? smallList + i : bigList + (i - cntSmall));
+      const int4 fc = __ldg(p.faces4 + f);
+      const float4 s0 = __ldg(vs + fc.x), s1 = __ldg(vs + fc.y), s2 = __ldg(vs + fc.z);
+      const float4 p0 = __ldg(pj + fc.x), p1 = __ldg(pj + fc.y), p2 = __ldg(pj + fc.z);
+      const int4 bb = bbox_exact(p0, p1, p2, p.W, p.H);
+      const int cx0 = max(bb.x, tileX0), cx1 = min(bb.z, tileX0 + TS - 1);
+      const int cy0 = max(bb.y, tileY0), cy1 = min(bb.w, tileY0 + TS - 1);
+      const int w = cx1 - cx0 + 1, h = cy1 - cy0 + 1;
+      if (w > 0 && h > 0) {
+        n = h;                 // work items are ROWS of the clipped bbox
+        const TriSetup ts = tri_setup_exact(mk3(s0.x, s0.y, s0.z), mk3(s1.x, s1.y, s1.z), mk3(s2.x, s2.y, s2.z), ros);
+        mine.v0x = ts.v0.x; mine.v0y = ts.v0.y; mine.v0z = ts.v0.z;
+        mine.v1x = ts.v1.x; mine.v1y = ts.v1.y; mine.v1z = ts.v1.z;
+        mine.v2x = ts.v2.x; mine.v2y = ts.v2.y; mine.v2z = ts.v2.z;
+        mine.Nx = ts.N.x; mine.Ny = ts.N.y; mine.Nz = ts.N.z;
+        mine.num = ts.num; mine.den = ts.den; mine.z0 = p0.z; mine.z1 = p1.z; mine.z2 = p2.z;
+        mine.face = f; mine.pad0 = 0; mine.pad1 = 0;
+        edge_setup(p0, p1, p2, (float)tileX0, (float)tileY0, p.cullMargin, em);
+        em.geom = (cx0 - tileX0) | ((cy0 - tileY0) << 8) | (w << 16);
+        em.pad0 = 0; em.pad1 = 0;
+      }
+    }
+    // warp scan of the row counts: compacted rank + first row of every non-empty triangle
+    int rows = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL_MASK, rows, o); if (lane >= o) rows += y; }
+    const int nrows = __shfl_sync(FULL_MASK, rows, 31);
+    const unsigned nzt = __ballot_sync(FULL_MASK, n > 0);
+    const int ntri = __popc(nzt);
+    if (n > 0) {
+      const int rank = __popc(nzt & ((1u << lane) - 1u));
+      em.start = rows - n;
+      rec[rank] = mine;
+      erec[rank] = em;
+      startArr[rank] = em.start;
+    }
+    startArr[ntri + lane] = 0x7fffffff;
+    if (lane == 0) startArr[ntri + 32] = 0x7fffffff;
+    __syncwarp();
+    int K0 = 0;
+    for (int fb = 0; fb < nrows; fb += 32) {
+      // (1) one bbox row per lane: which triangle, which row
+      const int s = startArr[K0 + 1 + lane];
+      const unsigned bits = (s < fb + 32) ? (1u << (s - fb)) : 0u;
+      const unsigned mask = __reduce_or_sync(FULL_MASK, bits);
+      const int k = K0 + __popc(mask & ((2u << lane) - 1u));
+      K0 += __popc(mask);
+      const int fr = fb + lane;
+      // (2) conservative x-span of the row: pixels outside it provably fail the exact test
+      int cnt = 0, info = 0;
+      if (fr < nrows) {
+        const float4* ep = reinterpret_cast<const float4*>(&erec[k]);
+        const float4 e0 = ep[0], e1 = ep[1], e2 = ep[2];
+        const int4 e3 = reinterpret_cast<const int4*>(ep)[3];
+        const int x0 = e3.y & 0xff, ly = ((e3.y >> 8) & 0xff) + (fr - e3.x), w = e3.y >> 16;
+        const float fy = (float)ly;
+        const float s0 = fmaf(e0.y, fy, e0.z), s1 = fmaf(e1.x, fy, e1.y), s2 = fmaf(e1.w, fy, e2.x);
+        // A_i > 0: x >= t_i ; A_i < 0: x <= t_i ; A_i == 0: row kept iff s_i >= 0
+        float xlo = -1.0e30f, xhi = 1.0e30f;
+        bool ok = true;
+        { const float t = s0 * e2.y; if (e0.x > 0.f) xlo = fmaxf(xlo, t); else if (e0.x < 0.f) xhi = fminf(xhi, t); else ok = ok && (s0 >= 0.f); }
+        { const float t = s1 * e2.z; if (e0.w > 0.f) xlo = fmaxf(xlo, t); else if (e0.w < 0.f) xhi = fminf(xhi, t); else ok = ok && (s1 >= 0.f); }
+        { const float t = s2 * e2.w; if (e1.z > 0.f) xlo = fmaxf(xlo, t); else if (e1.z < 0.f) xhi = fminf(xhi, t); else ok = ok && (s2 >= 0.f); }
+        // 1e-3 px of slack for the rounding of t_i (|t| <= ~64 wherever it matters), then clamp to the bbox row
+        const int xl = max(x0, (int)ceilf(fmaxf(xlo - 1.0e-3f, -1.0f)));
+        const int xr = min(x0 + w - 1, (int)floorf(fminf(xhi + 1.0e-3f, 64.0f)));
+        cnt = ok ? max(0, xr - xl + 1) : 0;
+        info = (k << 10) | (ly << 5) | xl;
+      }
+      // (3) compact the non-empty spans of these 32 rows, (4) expand them 32 pixels at a time
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += y; }
+      const int total = __shfl_sync(FULL_MASK, incl, 31);
+      const unsigned nz = __ballot_sync(FULL_MASK, cnt > 0);
+      const int nspan = __popc(nz);
+      if (cnt > 0) {
+        const int r = __popc(nz & ((1u << lane) - 1u));
+        mySpanStart[r] = incl - cnt;
+        mySpanInfo[r] = info;
+      }
+      mySpanStart[nspan + lane] = 0x7fffffff;
+      if (lane == 0) mySpanStart[nspan + 32] = 0x7fffffff;
+      __syncwarp();
+      int S0 = 0;
+      for (int t0 = 0; t0 < total; t0 += 32) {
+        const int ss = mySpanStart[S0 + 1 + lane];
+        const unsigned sb = (ss < t0 + 32) ? (1u << (ss - t0)) : 0u;
+        const unsigned sm = __reduce_or_sync(FULL_MASK, sb);
+        const int si = S0 + __popc(sm & ((2u << lane) - 1u));
+        S0 += __popc(sm);
+        const int t = t0 + lane;
+        if (t < total) {
+          const int inf = mySpanInfo[si];
+          exact_pair(inf >> 10, ((inf >> 5) & 31) * TS + (inf & 31) + (t - mySpanStart[si]));
         }
       }
-      // block-wide exclusive scan of (1 << SHIFT | n): rank among non-empty triangles + first fragment
-      const int packed = n > 0 ? ((1 << SHIFT) | n) : 0;
-      int x = packed;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL_MASK, x, o); if (lane >= o) x += y; }
-      if (lane == 31) warpTot[warp] = x;
-      __syncthreads();
-      int before = 0, total = 0;
-#pragma unroll
-      for (int wi = 0; wi < 8; ++wi) { const int t = warpTot[wi]; if (wi < warp) before += t; total += t; }
-      const int excl = before + x - packed;
-      const int ntri = total >> SHIFT, nfrag = total & ((1 << SHIFT) - 1);
-      if (n > 0) {
-        const int rank = excl >> SHIFT;
-        em.start = excl & ((1 << SHIFT) - 1);
-        rec[rank] = mine;
-        erec[rank] = em;
-        startArr[rank] = em.start;
-      }
-      if (tid < 40) startArr[ntri + tid] = 0x7fffffff;
-      __syncthreads();
-      if (nfrag == 0) continue;
-
-      // rows [0, nfrag) are split evenly over the 8 warps (32-aligned), whatever the triangle sizes
-      const int per = ((nfrag + 7) / 8 + 31) & ~31;
-      const int lo = warp * per, hi = min(lo + per, nfrag);
-      if (lo < hi) {
-        int c0 = 0;
-        for (int j = lane; j < ntri; j += 32) c0 += (startArr[j] <= lo) ? 1 : 0;
-        int K0 = __reduce_add_sync(FULL_MASK, c0) - 1;   // triangle owning row `lo`
-        for (int fb = lo; fb < hi; fb += 32) {
-          // (1) one bbox row per lane: which triangle, which row
-          const int s = startArr[K0 + 1 + lane];
-          const unsigned bits = (s < fb + 32) ? (1u << (s - fb)) : 0u;
-          const unsigned mask = __reduce_or_sync(FULL_MASK, bits);
-          const int k = K0 + __popc(mask & ((2u << lane) - 1u));
-          K0 += __popc(mask);
-          const int fr = fb + lane;
-          // (2) conservative x-span of the row: pixels outside it provably fail the exact test
-          int cnt = 0, info = 0;
-          if (fr < hi) {
-            const float4* ep = reinterpret_cast<const float4*>(&erec[k]);
-            const float4 e0 = ep[0], e1 = ep[1], e2 = ep[2];
-            const int4 e3 = reinterpret_cast<const int4*>(ep)[3];
-            const int x0 = e3.y & 0xff, ly = ((e3.y >> 8) & 0xff) + (fr - e3.x), w = e3.y >> 16;
-            const float fy = (float)ly;
-            const float s0 = fmaf(e0.y, fy, e0.z), s1 = fmaf(e1.x, fy, e1.y), s2 = fmaf(e1.w, fy, e2.x);
-            // A_i > 0: x >= t_i ; A_i < 0: x <= t_i ; A_i == 0: row kept iff s_i >= 0
-            float xlo = -1.0e30f, xhi = 1.0e30f;
-            bool ok = true;
-            { const float t = s0 * e2.y; if (e0.x > 0.f) xlo = fmaxf(xlo, t); else if (e0.x < 0.f) xhi = fminf(xhi, t); else ok = ok && (s0 >= 0.f); }
-            { const float t = s1 * e2.z; if (e0.w > 0.f) xlo = fmaxf(xlo, t); else if (e0.w < 0.f) xhi = fminf(xhi, t); else ok = ok && (s1 >= 0.f); }
-            { const float t = s2 * e2.w; if (e1.z > 0.f) xlo = fmaxf(xlo, t); else if (e1.z < 0.f) xhi = fminf(xhi, t); else ok = ok && (s2 >= 0.f); }
-            // 1e-3 px of slack for the rounding of t_i (|t| <= ~64 wherever it matters), then clamp to the bbox row
-            const int xl = max(x0, (int)ceilf(fmaxf(xlo - 1.0e-3f, -1.0f)));
-            const int xr = min(x0 + w - 1, (int)floorf(fminf(xhi + 1.0e-3f, 64.0f)));
-            cnt = ok ? max(0, xr - xl + 1) : 0;
-            info = (k << 10) | (ly << 5) | xl;
-          }
-          // (3) compact the non-empty spans of these 32 rows, (4) expand them 32 pixels at a time
-          int incl = cnt;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += y; }
-          const int total = __shfl_sync(FULL_MASK, incl, 31);
-          const unsigned nz = __ballot_sync(FULL_MASK, cnt > 0);
-          const int nspan = __popc(nz);
-          if (cnt > 0) {
-            const int r = __popc(nz & ((1u << lane) - 1u));
-            mySpanStart[r] = incl - cnt;
-            mySpanInfo[r] = info;
-          }
-          mySpanStart[nspan + lane] = 0x7fffffff;
-          if (lane == 0) mySpanStart[nspan + 32] = 0x7fffffff;
-          __syncwarp();
-          int S0 = 0;
-          for (int t0 = 0; t0 < total; t0 += 32) {
-            const int ss = mySpanStart[S0 + 1 + lane];
-            const unsigned sb = (ss < t0 + 32) ? (1u << (ss - t0)) : 0u;
-            const unsigned sm = __reduce_or_sync(FULL_MASK, sb);
-            const int si = S0 + __popc(sm & ((2u << lane) - 1u));
-            S0 += __popc(sm);
-            const int t = t0 + lane;
-            if (t < total) {
-              const int inf = mySpanInfo[si];
-              exact_pair(inf >> 10, ((inf >> 5) & 31) * TS + (inf & 31) + (t - mySpanStart[si]));
-            }
-          }
-          __syncwarp();
-        }
-      }
+      __syncwarp();
     }
   }
   __syncthreads();
@@ -674,10 +686,11 @@ int launch_camera(const float* extr, const float* intr, CamRec* cams, int* bigCo
 }
 
 int launch_vertex(const FwdArgs& a, cudaStream_t st) {
-  vertex_kernel<<<dim3((a.N + 127) / 128, a.B), 128, 0, st>>>(a.vertex_pos, a.vertex_color, a.faces4, a.vfOffsets, a.vfList,
+  if (a.F > 0) face_normal_kernel<<<dim3((a.F + 255) / 256, a.B), 256, 0, st>>>(a.vertex_pos, a.faces4, a.s.fnorm4, a.N, a.F);
+  vertex_kernel<<<dim3((a.N + 127) / 128, a.B), 128, 0, st>>>(a.vertex_pos, a.vertex_color, a.s.fnorm4, a.vfOffsets, a.vfList,
                                                              a.s.cams, a.s.proj, a.s.vscaled, a.s.vnorm4, a.s.vcol4,
-                                                             a.vertex_normal, a.N, a.C);
-  return 1;
+                                                             a.vertex_normal, a.N, a.F, a.C);
+  return a.F > 0 ? 2 : 1;
 }
 
 int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
@@ -686,11 +699,8 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   int launches = launch_camera(a.extrinsics, a.intrinsics, a.s.cams, a.s.bigCount, V, st);
   tm->end(st);
   tm->begin(K_VERTEX, st);
-  vertex_kernel<<<dim3((a.N + 127) / 128, a.B), 128, 0, st>>>(a.vertex_pos, a.vertex_color, a.faces4, a.vfOffsets, a.vfList,
-                                                             a.s.cams, a.s.proj, a.s.vscaled, a.s.vnorm4, a.s.vcol4,
-                                                             a.vertex_normal, a.N, a.C);
+  launches += launch_vertex(a, st);   // face normals + per-vertex work
   tm->end(st);
-  ++launches;
   const int tileShift = a.tile == 32 ? 5 : 4;
   const dim3 gridF((a.F + 255) / 256, V);
   tm->begin(K_BIN_COUNT, st);
@@ -727,8 +737,14 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin;
   const dim3 gridT((unsigned)a.nT * (unsigned)V);
   tm->begin(K_RASTER, st);
-  if (a.tile == 16) raster_kernel<16><<<gridT, 256, 0, st>>>(p);
-  else raster_kernel<32><<<gridT, 256, 0, st>>>(p);
+  static bool attrSet = false;
+  if (!attrSet) {   // > 48 KB of dynamic shared memory needs the opt-in (once per process and device function)
+    cudaFuncSetAttribute(raster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<16>());
+    cudaFuncSetAttribute(raster_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<32>());
+    attrSet = true;
+  }
+  if (a.tile == 16) raster_kernel<16><<<gridT, 256, raster_smem_bytes<16>(), st>>>(p);
+  else raster_kernel<32><<<gridT, 256, raster_smem_bytes<32>(), st>>>(p);
   tm->end(st);
   ++launches;
   return launch_ok() ? launches : -1;

@@ -18,6 +18,7 @@ struct Scratch {
   CamRec* cams = nullptr;        // [V]
   float4* proj = nullptr;        // [V*N]  (x/z, y/z, z, 0)
   float4* vscaled = nullptr;     // [B*N]  vertex / 1000 (div.rn), w = 0
+  float4* fnorm4 = nullptr;      // [B*F]  face normal cross(v1-v0, v2-v0)
   float4* vnorm4 = nullptr;      // [B*N]  unnormalised vertex normal
   float4* vcol4 = nullptr;       // [B*N]  vertex colour
   int* tileCount = nullptr;      // [V*nT] self-cleaning (the raster kernel zeroes its own entry)
