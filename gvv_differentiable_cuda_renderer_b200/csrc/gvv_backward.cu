@@ -387,11 +387,15 @@ struct PrepArgs {
   const float *vertex_pos, *vertex_color, *vertex_normal;
   float4 *pos4, *col4, *nor4;
   long long nBN, nVN;
+  const float *extr, *intr;
+  CamRec* cams;
+  int V;
 };
 
 __global__ void prep_kernel(PrepArgs a) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t0 < a.V) fill_camrec(a.extr, a.intr, a.cams, (int)t0);   // camera records for pixel_grad_kernel (ref :17-61)
   for (long long i = t0; i < a.nBN; i += stride) {
     a.pos4[i] = make_float4(__ldg(a.vertex_pos + 3 * i), __ldg(a.vertex_pos + 3 * i + 1), __ldg(a.vertex_pos + 3 * i + 2), 0.f);
     if (a.vertex_color) a.col4[i] = make_float4(__ldg(a.vertex_color + 3 * i), __ldg(a.vertex_color + 3 * i + 1), __ldg(a.vertex_color + 3 * i + 2), 0.f);
@@ -448,9 +452,7 @@ int launch_camera(const float* extr, const float* intr, CamRec* cams, int* bigCo
 
 int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const int V = a.B * a.C;
-  tm->begin(K_CAMERA, st);
-  int launches = launch_camera(a.extrinsics, a.intrinsics, a.s.cams, nullptr, V, st);
-  tm->end(st);
+  int launches = 0;
   ZeroArgs z;
   const long long nv = (long long)a.B * a.N * 3;
   z.p[0] = a.vpos_grad; z.n[0] = nv;
@@ -463,6 +465,7 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   pa.vertex_pos = a.vertex_pos; pa.vertex_color = a.vertex_color; pa.vertex_normal = a.vertex_normal;
   pa.pos4 = a.s.bpos4; pa.col4 = a.s.bcol4; pa.nor4 = a.s.bnor4;
   pa.nBN = (long long)a.B * a.N; pa.nVN = (long long)V * a.N;
+  pa.extr = a.extrinsics; pa.intr = a.intrinsics; pa.cams = a.s.cams; pa.V = V;
   tm->begin(K_ZERO, st);
   prep_kernel<<<148 * 8, 256, 0, st>>>(pa);
   tm->end(st);

@@ -54,6 +54,29 @@ __device__ __forceinline__ void camera_inverse_exact(const float* __restrict__ K
 #include "cam_inverse_exact.inc"
 }
 
+// One view's camera record: initializeCamerasDevice (CUDABasedRasterization.cu:23-67) + the ray origin.
+__device__ __forceinline__ void fill_camrec(const float* __restrict__ extr, const float* __restrict__ intr, CamRec* __restrict__ cams, int v) {
+  float K[9], E[12], Einv[16], Pinv[16];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) K[i] = intr[v * 9 + i];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) E[i] = extr[v * 12 + i];
+  camera_inverse_exact(K, E, Einv, Pinv);
+  CamRec& r = cams[v];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) r.K[i] = K[i];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) r.E[i] = E[i];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { r.Einv[i] = Einv[i]; r.Pinv[i] = Pinv[i]; }
+  // o = 4th column of E^-1, o /= o.w (CameraUtil.h:253-255); ros = o / 1000 (RendererUtil.h:32)
+  const float ox = __fdiv_rn(Einv[3], Einv[15]);
+  const float oy = __fdiv_rn(Einv[7], Einv[15]);
+  const float oz = __fdiv_rn(Einv[11], Einv[15]);
+  r.ro[0] = ox; r.ro[1] = oy; r.ro[2] = oz;
+  r.ros[0] = __fdiv_rn(ox, 1000.f); r.ros[1] = __fdiv_rn(oy, 1000.f); r.ros[2] = __fdiv_rn(oz, 1000.f);
+}
+
 // Reference: getRayCuda2 + backprojectPixelCuda (CameraUtil.h:223-236,251-258).
 // px,py = pixel centre (u+0.5, v+0.5).  Returns the normalised world-space direction.
 __device__ __forceinline__ F3 ray_dir_exact(const float* __restrict__ Pinv, const float* __restrict__ ro, float px, float py) {

@@ -30,25 +30,7 @@ __global__ void camera_kernel(const float* __restrict__ extr, const float* __res
                               CamRec* __restrict__ cams, int* __restrict__ bigCount, int V) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= V) return;
-  float K[9], E[12], Einv[16], Pinv[16];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) K[i] = intr[v * 9 + i];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) E[i] = extr[v * 12 + i];
-  camera_inverse_exact(K, E, Einv, Pinv);
-  CamRec& r = cams[v];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) r.K[i] = K[i];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) r.E[i] = E[i];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { r.Einv[i] = Einv[i]; r.Pinv[i] = Pinv[i]; }
-  // o = 4th column of E^-1, o /= o.w (CameraUtil.h:253-255); ros = o / 1000 (RendererUtil.h:32)
-  const float ox = __fdiv_rn(Einv[3], Einv[15]);
-  const float oy = __fdiv_rn(Einv[7], Einv[15]);
-  const float oz = __fdiv_rn(Einv[11], Einv[15]);
-  r.ro[0] = ox; r.ro[1] = oy; r.ro[2] = oz;
-  r.ros[0] = __fdiv_rn(ox, 1000.f); r.ros[1] = __fdiv_rn(oy, 1000.f); r.ros[2] = __fdiv_rn(oz, 1000.f);
+  fill_camrec(extr, intr, cams, v);
   if (bigCount) bigCount[v] = 0;
 }
 
@@ -75,11 +57,14 @@ face_normal_kernel(const float* __restrict__ vertex_pos, const int4* __restrict_
 __global__ void __launch_bounds__(128)
 vertex_kernel(const float* __restrict__ vertex_pos, const float* __restrict__ vertex_color,
               const float4* __restrict__ fnorm4, const int* __restrict__ vfOffsets, const int* __restrict__ vfList,
-              const CamRec* __restrict__ cams, float4* __restrict__ proj, float4* __restrict__ vscaled,
+              const float* __restrict__ extr, const float* __restrict__ intr, int* __restrict__ bigCount,
+              float4* __restrict__ proj, float4* __restrict__ vscaled,
               float4* __restrict__ vnorm4, float4* __restrict__ vcol4, float* __restrict__ vertex_normal_out,
               int N, int F, int C) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
+  if (blockIdx.x == 0)   // consumed by bin_count_kernel (next launch)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) bigCount[b * C + c] = 0;
   if (n >= N) return;
   const float* pos = vertex_pos + (size_t)b * N * 3;
   const F3 p = ld3(pos, n);
@@ -103,8 +88,7 @@ vertex_kernel(const float* __restrict__ vertex_pos, const float* __restrict__ ve
     const int view = b * C + c;
     float* vn = vertex_normal_out + ((size_t)view * N + n) * 3;
     vn[0] = nrm.x; vn[1] = nrm.y; vn[2] = nrm.z;
-    const CamRec* cam = cams + view;
-    proj[(size_t)view * N + n] = project_exact(cam->K, cam->E, p.x, p.y, p.z);
+    proj[(size_t)view * N + n] = project_exact(intr + view * 9, extr + view * 12, p.x, p.y, p.z);
   }
 }
 
@@ -164,7 +148,9 @@ bin_count_kernel(const int4* __restrict__ faces4, const float4* __restrict__ pro
 // CTAs visit the tiles: heaviest bins first (longest-processing-time-first keeps the silhouette
 // tiles, which hold ~10x the average work, out of the tail of the launch)
 __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ tileCount, int* __restrict__ tileOffset,
-                                                        int* __restrict__ tileOrder, int nT) {
+                                                        int* __restrict__ tileOrder, int nT,
+                                                        const float* __restrict__ extr, const float* __restrict__ intr,
+                                                        CamRec* __restrict__ cams) {
   __shared__ int warpSum[32];
   __shared__ int carry;
   __shared__ int bucketStart[33], bucketFill[33];
@@ -211,6 +197,9 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
     const int k = c > 0 ? 32 - __clz(c) : 0;
     tileOrder[(size_t)view * nT + bucketStart[k] + atomicAdd(&bucketFill[k], 1)] = i;
   }
+  // one block per view: its spare time also produces the view's camera record (E^-1, (KE)^-1, ray
+  // origin) for the raster kernel -- the reference spends a <<<1,1>>> launch on this
+  if (threadIdx.x == 0) fill_camrec(extr, intr, cams, view);
 }
 
 template <bool SMEM_HIST>
@@ -688,16 +677,15 @@ int launch_camera(const float* extr, const float* intr, CamRec* cams, int* bigCo
 int launch_vertex(const FwdArgs& a, cudaStream_t st) {
   if (a.F > 0) face_normal_kernel<<<dim3((a.F + 255) / 256, a.B), 256, 0, st>>>(a.vertex_pos, a.faces4, a.s.fnorm4, a.N, a.F);
   vertex_kernel<<<dim3((a.N + 127) / 128, a.B), 128, 0, st>>>(a.vertex_pos, a.vertex_color, a.s.fnorm4, a.vfOffsets, a.vfList,
-                                                             a.s.cams, a.s.proj, a.s.vscaled, a.s.vnorm4, a.s.vcol4,
+                                                             a.extrinsics, a.intrinsics, a.s.bigCount,
+                                                             a.s.proj, a.s.vscaled, a.s.vnorm4, a.s.vcol4,
                                                              a.vertex_normal, a.N, a.F, a.C);
   return a.F > 0 ? 2 : 1;
 }
 
 int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const int V = a.B * a.C;
-  tm->begin(K_CAMERA, st);
-  int launches = launch_camera(a.extrinsics, a.intrinsics, a.s.cams, a.s.bigCount, V, st);
-  tm->end(st);
+  int launches = 0;
   tm->begin(K_VERTEX, st);
   launches += launch_vertex(a, st);   // face normals + per-vertex work
   tm->end(st);
@@ -714,7 +702,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   tm->end(st);
   ++launches;
   tm->begin(K_BIN_SCAN, st);
-  bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.nT);
+  bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.nT, a.extrinsics, a.intrinsics, a.s.cams);
   tm->end(st);
   ++launches;
   tm->begin(K_BIN_FILL, st);
