@@ -190,6 +190,7 @@ extern "C" int gvv_set_option(gvv_handle h, const char* key, int32_t value) {
     h->cullMargin = value < 0 ? -1.f : (float)value / 1000.f;
     return GVV_OK;
   }
+  if (!strcmp(key, "ray_cache")) { h->rayCache = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "time_kernels")) {
     KernelTimer& t = h->timer;
     cudaSetDevice(h->device);
@@ -230,7 +231,7 @@ extern "C" int gvv_forward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
   FwdArgs a;
   a.B = B; a.C = h->C; a.N = h->N; a.F = h->F; a.W = h->W; a.H = h->H; a.texH = texH; a.texW = texW;
   a.albedo = h->albedo; a.shading = h->shading;
-  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin;
+  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin; a.rayCache = h->rayCache;
   a.vertex_pos = vertex_pos; a.vertex_color = vertex_color; a.texture = texture; a.sh_coeff = sh_coeff;
   a.extrinsics = extrinsics; a.intrinsics = intrinsics; a.texcoords = h->texcoords;
   a.faces4 = h->faces4; a.vfOffsets = h->vfOffsets; a.vfList = h->vfList;

@@ -141,7 +141,7 @@ __device__ __forceinline__ void bary_vjp_fast(V3 o, V3 d, V3 v0, V3 v1, V3 v2, f
 __device__ __forceinline__ V3 ld4(const float4* __restrict__ p, size_t i) { const float4 v = __ldg(p + i); return v3(v.x, v.y, v.z); }
 
 // grid (W/32, H/8, V), 256 threads: warp w owns the 32-pixel scanline segment y = 8*by + w.
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 pixel_grad_kernel(const PixelParams p) {
   __shared__ __align__(16) float buf[8][kVals * kRow];   // per warp: value-major, kRow floats per value (32 pixels + pad)
   __shared__ float shPart[8][kVals];
@@ -157,10 +157,11 @@ pixel_grad_kernel(const PixelParams p) {
   const bool covered = face >= 0;
   const bool shaded = p.shading == GVV_SHADING_SHADED;
 
-  if (__syncthreads_or(covered) == 0) return;   // nothing visible in this 32x8 block
-  if (tid < 64) reinterpret_cast<float*>(&cam)[tid] = reinterpret_cast<const float*>(p.cams + view)[tid];
-  if (tid >= 64 && tid < 64 + 27) shc[tid - 64] = p.sh_coeff[(size_t)view * 27 + (tid - 64)];
-  __syncthreads();
+  // camera + SH staging overlaps the latency of the face load; ONE barrier publishes both and
+  // tells whether anything is visible in this 32x8 block
+  if (tid < 64) reinterpret_cast<float*>(&cam)[tid] = __ldg(reinterpret_cast<const float*>(p.cams + view) + tid);
+  if (tid >= 64 && tid < 64 + 27) shc[tid - 64] = __ldg(p.sh_coeff + (size_t)view * 27 + (tid - 64));
+  if (__syncthreads_or(covered) == 0) return;
 
   float* mybuf = buf[warp];
   float* mine = mybuf + lane;   // value j of this lane's pixel lives at mine[j * kRow]

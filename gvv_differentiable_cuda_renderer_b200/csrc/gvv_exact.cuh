@@ -123,14 +123,12 @@ __device__ __forceinline__ bool hit_exact(const TriSetup& t, F3 ros, F3 rd, floa
   const float tt = __fdiv_rn(t.num, nd);
   if (tt < 0.f) return false;
   const F3 P = mk3(__fmaf_rn(rd.x, tt, ros.x), __fmaf_rn(rd.y, tt, ros.y), __fmaf_rn(rd.z, tt, ros.z));
-  const F3 e0 = sub3(t.v1, t.v0);
-  if (dot3x(t.N, cross3x(e0, sub3(P, t.v0))) < 0.f) return false;
-  const F3 e1 = sub3(t.v2, t.v1);
-  const float an = dot3x(t.N, cross3x(e1, sub3(P, t.v1)));
-  if (an < 0.f) return false;
-  const F3 e2 = sub3(t.v0, t.v2);
-  const float bn = dot3x(t.N, cross3x(e2, sub3(P, t.v2)));
-  if (bn < 0.f) return false;
+  // the three edge functions are evaluated together (independent chains, more ILP); the reference
+  // rejects on them one after the other -- same values, same decision
+  const float e0n = dot3x(t.N, cross3x(sub3(t.v1, t.v0), sub3(P, t.v0)));
+  const float an = dot3x(t.N, cross3x(sub3(t.v2, t.v1), sub3(P, t.v1)));
+  const float bn = dot3x(t.N, cross3x(sub3(t.v0, t.v2), sub3(P, t.v2)));
+  if (e0n < 0.f || an < 0.f || bn < 0.f) return false;
   a = __fdiv_rn(an, t.den);
   b = __fdiv_rn(bn, t.den);
   c = __fsub_rn(__fsub_rn(1.f, a), b);

@@ -370,13 +370,15 @@ __device__ __forceinline__ float sh_eval(const float* __restrict__ sh, F3 n) {
 // Shared-memory plan of raster_kernel (dynamic, carved by hand):
 //   zt[TS*TS] u64 | rayx,rayy,rayz[TS*TS] f32 | per warp: rec[32], erec[32], startArr[68], spanStart[68], spanInfo[32]
 constexpr int kWarpSmemBytes = 32 * (int)sizeof(TriRec) + 32 * (int)sizeof(EdgeRec) + (68 + 68 + 32) * 4;
-template <int TS>
-constexpr int raster_smem_bytes() { return TS * TS * (8 + 12) + 8 * kWarpSmemBytes; }
+// RC = per-pixel ray cache in shared memory (3 CTAs/SM) or rays recomputed per use (4 CTAs/SM, <= 64 registers)
+template <int TS, bool RC>
+constexpr int raster_smem_bytes() { return TS * TS * (8 + (RC ? 12 : 0)) + 8 * kWarpSmemBytes; }
 
-template <int TS>
-__global__ void __launch_bounds__(256, 3)
+template <int TS, bool RC>
+__global__ void __launch_bounds__(256, RC ? 3 : 4)
 raster_kernel(const RasterParams p) {
   constexpr int NPIX = TS * TS;
+  constexpr int ZRAY = NPIX * (8 + (RC ? 12 : 0));
   extern __shared__ __align__(16) unsigned char smemRaw[];
   unsigned long long* zt = reinterpret_cast<unsigned long long*>(smemRaw);
   float* rayx = reinterpret_cast<float*>(smemRaw + NPIX * 8);
@@ -421,15 +423,21 @@ raster_kernel(const RasterParams p) {
   for (int q = tid; q < NPIX; q += 256) {
     zt[q] = kEmptyKey;
     const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
-    const F3 rd = ray_dir_exact(cam.Pinv, cam.ro, __fadd_rn((float)x, 0.5f), __fadd_rn((float)y, 0.5f));
-    rayx[q] = rd.x; rayy[q] = rd.y; rayz[q] = rd.z;
+    if (RC) {
+      const F3 rd = ray_dir_exact(cam.Pinv, cam.ro, __fadd_rn((float)x, 0.5f), __fadd_rn((float)y, 0.5f));
+      rayx[q] = rd.x; rayy[q] = rd.y; rayz[q] = rd.z;
+    }
   }
   __syncthreads();
+  auto ray_of = [&](int q) {
+    if (RC) return mk3(rayx[q], rayy[q], rayz[q]);
+    return ray_dir_exact(cam.Pinv, cam.ro, __fadd_rn((float)(tileX0 + (q % TS)), 0.5f), __fadd_rn((float)(tileY0 + (q / TS)), 0.5f));
+  };
 
   // ---- rasterise.  Every warp works on its own: it grabs a batch of up to 32 triangles of the
   // tile's bin (then of the view's big-triangle list), sets them up into its private records, and
   // rasterises them; no block-wide barrier until all batches are done. ----
-  unsigned char* wbase = smemRaw + NPIX * 20 + warp * kWarpSmemBytes;
+  unsigned char* wbase = smemRaw + ZRAY + warp * kWarpSmemBytes;
   TriRec* rec = reinterpret_cast<TriRec*>(wbase);
   EdgeRec* erec = reinterpret_cast<EdgeRec*>(wbase + 32 * sizeof(TriRec));
   int* startArr = reinterpret_cast<int*>(wbase + 32 * (sizeof(TriRec) + sizeof(EdgeRec)));
@@ -444,7 +452,7 @@ raster_kernel(const RasterParams p) {
     TriSetup ts;
     ts.v0 = mk3(r0.x, r0.y, r0.z); ts.v1 = mk3(r0.w, r1.x, r1.y); ts.v2 = mk3(r1.z, r1.w, r2.x);
     ts.N = mk3(r2.y, r2.z, r2.w); ts.num = r3.x; ts.den = r3.y;
-    const F3 rd = mk3(rayx[q], rayy[q], rayz[q]);
+    const F3 rd = ray_of(q);
     float a, bq, c;
     if (hit_exact(ts, ros, rd, a, bq, c)) {
       const int depth = depth_key_exact(a, bq, c, r3.z, r3.w, __int_as_float(r4.x));
@@ -592,7 +600,7 @@ raster_kernel(const RasterParams p) {
       const int4 fc = __ldg(p.faces4 + faceId);
       float z0, z1, z2, c;
       const TriSetup ts = load_setup(p, b, view, fc, ros, z0, z1, z2, nullptr);
-      const F3 rd = mk3(rayx[q], rayy[q], rayz[q]);
+      const F3 rd = ray_of(q);
       hit_exact(ts, ros, rd, a, bq, c);   // same arithmetic as the rasterising pass => same (a,b,c)
       const float4 n0 = __ldg(vn + fc.x), n1 = __ldg(vn + fc.y), n2 = __ldg(vn + fc.z);
       F3 nr = mk3(interp3(a, bq, c, n0.x, n1.x, n2.x), interp3(a, bq, c, n0.y, n1.y, n2.y), interp3(a, bq, c, n0.z, n1.z, n2.z));
@@ -727,12 +735,19 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   tm->begin(K_RASTER, st);
   static bool attrSet = false;
   if (!attrSet) {   // > 48 KB of dynamic shared memory needs the opt-in (once per process and device function)
-    cudaFuncSetAttribute(raster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<16>());
-    cudaFuncSetAttribute(raster_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<32>());
+    cudaFuncSetAttribute(raster_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<16, true>());
+    cudaFuncSetAttribute(raster_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<32, true>());
+    cudaFuncSetAttribute(raster_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<16, false>());
+    cudaFuncSetAttribute(raster_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<32, false>());
     attrSet = true;
   }
-  if (a.tile == 16) raster_kernel<16><<<gridT, 256, raster_smem_bytes<16>(), st>>>(p);
-  else raster_kernel<32><<<gridT, 256, raster_smem_bytes<32>(), st>>>(p);
+  if (a.tile == 16) {
+    if (a.rayCache) raster_kernel<16, true><<<gridT, 256, raster_smem_bytes<16, true>(), st>>>(p);
+    else raster_kernel<16, false><<<gridT, 256, raster_smem_bytes<16, false>(), st>>>(p);
+  } else {
+    if (a.rayCache) raster_kernel<32, true><<<gridT, 256, raster_smem_bytes<32, true>(), st>>>(p);
+    else raster_kernel<32, false><<<gridT, 256, raster_smem_bytes<32, false>(), st>>>(p);
+  }
   tm->end(st);
   ++launches;
   return launch_ok() ? launches : -1;

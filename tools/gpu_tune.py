@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """GPU-box tuning probe: per-kernel times of config 2 for a few knob settings (prints JSON lines).
-Extra settings: `python tools/gpu_tune.py 32,8 16,8` (tile,margin_milli)."""
+Own settings: `python tools/gpu_tune.py 32,62,1 32,62,0` (tile,margin_milli,ray_cache)."""
 import json, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,10 +12,14 @@ N, C, W, H = sc["num_vertices"], 8, 1024, 1024
 ins = [T(sc[k]) for k in ("vertex_pos", "vertex_color", "texture", "sh_coeff", "target_image", "extrinsics", "intrinsics")]
 G = torch.randn((1, C, H, W, 3), generator=torch.Generator().manual_seed(3)).to(dev)
 ref = None
-for tile, margin in [(32, -1), (32, 250), (32, 62), (32, 16), (16, 62), (16, 250)] + [tuple(map(int, a.split(","))) for a in sys.argv[1:]]:
+configs = [(32, -1, 1), (32, 250, 1), (32, 62, 1), (32, 16, 1), (16, 62, 1), (16, 250, 1)]
+if len(sys.argv) > 1:
+    configs = [(32, -1, 1)] + [tuple(map(int, a.split(","))) for a in sys.argv[1:]]   # tile,margin_milli,ray_cache
+for tile, margin, rc in configs:
     r = _native.NativeRenderer(sc["faces"], sc["texcoords"], N, C, W, H, "vertexColor", "shaded", 1, 1, False, dev)
     r.set_option("tile", tile)
     r.set_option("cull_margin_milli", margin)
+    r.set_option("ray_cache", rc)
     for _ in range(3):
         out = r.forward(*ins)
         r.backward(G, None, ins[0], ins[1], ins[2], ins[3], ins[4], out[3], out[0], out[1], ins[5], ins[6])
@@ -28,5 +32,5 @@ for tile, margin in [(32, -1), (32, 250), (32, 62), (32, 16), (16, 62), (16, 250
         ref = (out[1].clone(), out[0].clone(), out[2].clone())
     same = bool(torch.equal(out[1], ref[0]) and torch.equal(out[0].view(torch.int32), ref[1].view(torch.int32))
                 and torch.equal(out[2].view(torch.int32), ref[2].view(torch.int32)))
-    print(json.dumps({"tile": tile, "margin_milli": margin, "identical_to_unculled": same, "ms": kt}), flush=True)
+    print(json.dumps({"tile": tile, "margin_milli": margin, "ray_cache": rc, "identical_to_unculled": same, "ms": kt}), flush=True)
     r.close()
