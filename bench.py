@@ -183,6 +183,8 @@ def run_ours(args, rank, world, local_rank):
     h2d = sum(t.numel() * 4 for t in host.values())
     d2h = sum(t.numel() * 4 for t in out_host.values()) + 4
 
+    Gflat = G.reshape(-1)
+
     def e2e_step():
         d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         for k in ("vertex_pos", "vertex_color", "sh_coeff"):
@@ -192,7 +194,7 @@ def run_ours(args, rank, world, local_rank):
                                 shadingMode_attr="shaded", vertexPos_input=d["vertex_pos"], vertexColor_input=d["vertex_color"],
                                 texture_input=ins[2], shCoeff_input=d["sh_coeff"], targetImage_input=ins[4],
                                 extrinsics_input=d["extrinsics"], intrinsics_input=d["intrinsics"], device=dev)
-        loss = (layer.getRenderBufferTF() * G).sum()
+        loss = torch.dot(layer.getRenderBufferTF().reshape(-1), Gflat)   # d loss / d render = G (N(0,1), seed 3), one pass over the image
         loss.backward()
         if world > 1:
             sharding.allreduce_shared_grads([d["sh_coeff"].grad, d["vertex_color"].grad])

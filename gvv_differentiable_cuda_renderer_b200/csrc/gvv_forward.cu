@@ -338,7 +338,7 @@ struct RasterParams {
   int* tileCount; int* tileCursor; const int* tileOffset; const int* tileOrder; const int* bigCount; const int* bigList; const int* bins;
   const float* texture; const float* texcoords; const float* sh_coeff;
   float* bary; int32_t* face; float* render;
-  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, V;
+  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, V, batchDiv;
   float cullMargin;
 };
 
@@ -371,11 +371,12 @@ __device__ __forceinline__ float sh_eval(const float* __restrict__ sh, F3 n) {
 //   zt[TS*TS] u64 | rayx,rayy,rayz[TS*TS] f32 | per warp: rec[32], erec[32], startArr[68], spanStart[68], spanInfo[32]
 constexpr int kWarpSmemBytes = 32 * (int)sizeof(TriRec) + 32 * (int)sizeof(EdgeRec) + (68 + 68 + 32) * 4;
 // RC = per-pixel ray cache in shared memory (3 CTAs/SM) or rays recomputed per use (4 CTAs/SM, <= 64 registers)
-template <int TS, bool RC>
-constexpr int raster_smem_bytes() { return TS * TS * (8 + (RC ? 12 : 0)) + 8 * kWarpSmemBytes; }
+// NTH = threads per tile CTA (256 or 128)
+template <int TS, bool RC, int NTH>
+constexpr int raster_smem_bytes() { return TS * TS * (8 + (RC ? 12 : 0)) + (NTH / 32) * kWarpSmemBytes; }
 
-template <int TS, bool RC>
-__global__ void __launch_bounds__(256, RC ? 3 : 4)
+template <int TS, bool RC, int NTH>
+__global__ void __launch_bounds__(NTH, (RC ? 3 : 4) * (256 / NTH))
 raster_kernel(const RasterParams p) {
   constexpr int NPIX = TS * TS;
   constexpr int ZRAY = NPIX * (8 + (RC ? 12 : 0));
@@ -401,7 +402,7 @@ raster_kernel(const RasterParams p) {
 
   if (cntSmall == 0 && cntBig == 0) {
     // empty tile: background only (face -1, bary 0, render (0,1,0): initializeDevice :80-89)
-    for (int q = tid; q < NPIX; q += 256) {
+    for (int q = tid; q < NPIX; q += NTH) {
       const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
       if (x < p.W && y < p.H) {
         const size_t pix = pixBase + (size_t)y * p.W + x;
@@ -415,12 +416,12 @@ raster_kernel(const RasterParams p) {
 
   if (tid < 64) reinterpret_cast<float*>(&cam)[tid] = reinterpret_cast<const float*>(p.cams + view)[tid];
   if (tid >= 64 && tid < 64 + 27) shc[tid - 64] = p.sh_coeff[(size_t)view * 27 + (tid - 64)];
-  if (tid == 128) nextBatch = 0;
+  if (tid == 96) nextBatch = 0;
   __syncthreads();
   const F3 ros = mk3(cam.ros[0], cam.ros[1], cam.ros[2]);
 
   // z-tile clear + per-pixel ray cache (the ray depends on pixel and camera only)
-  for (int q = tid; q < NPIX; q += 256) {
+  for (int q = tid; q < NPIX; q += NTH) {
     zt[q] = kEmptyKey;
     const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
     if (RC) {
@@ -467,7 +468,7 @@ raster_kernel(const RasterParams p) {
   };
 
   const int cntAll = cntSmall + cntBig;
-  const int G = min(32, max(1, (cntAll + 7) / 8));      // triangles per batch: few big ones are spread over the warps
+  const int G = min(32, max(1, (cntAll + p.batchDiv - 1) / p.batchDiv));   // triangles per batch: a short bin is spread over the warps
   const int* smallList = p.bins + (size_t)view * p.F * kMaxSmallTiles + p.tileOffset[tidx];
   const int* bigList = p.bigList + (size_t)view * p.F;
   const float4* vs = p.vscaled + (size_t)b * p.N;
@@ -588,7 +589,7 @@ raster_kernel(const RasterParams p) {
   const float4* vn = p.vnorm4 + (size_t)b * p.N;
   const float4* vc = p.vcol4 + (size_t)b * p.N;
   const bool doShade = (p.shading == GVV_SHADING_SHADED && p.albedo != GVV_ALBEDO_NORMAL) || p.albedo == GVV_ALBEDO_LIGHTING;
-  for (int q = tid; q < NPIX; q += 256) {
+  for (int q = tid; q < NPIX; q += NTH) {
     const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
     if (x >= p.W || y >= p.H) continue;
     const size_t pix = pixBase + (size_t)y * p.W + x;
@@ -730,24 +731,28 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   p.texture = a.texture; p.texcoords = a.texcoords; p.sh_coeff = a.sh_coeff;
   p.bary = a.bary; p.face = a.face; p.render = a.render;
   p.C = a.C; p.N = a.N; p.F = a.F; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
-  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin;
+  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv;
   const dim3 gridT((unsigned)a.nT * (unsigned)V);
   tm->begin(K_RASTER, st);
   static bool attrSet = false;
   if (!attrSet) {   // > 48 KB of dynamic shared memory needs the opt-in (once per process and device function)
-    cudaFuncSetAttribute(raster_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<16, true>());
-    cudaFuncSetAttribute(raster_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<32, true>());
-    cudaFuncSetAttribute(raster_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<16, false>());
-    cudaFuncSetAttribute(raster_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<32, false>());
+#define GVV_RASTER_ATTR(TS, RC, NTH) cudaFuncSetAttribute(raster_kernel<TS, RC, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<TS, RC, NTH>())
+    GVV_RASTER_ATTR(16, true, 256); GVV_RASTER_ATTR(32, true, 256); GVV_RASTER_ATTR(16, false, 256); GVV_RASTER_ATTR(32, false, 256);
+    GVV_RASTER_ATTR(16, false, 128); GVV_RASTER_ATTR(32, false, 128);
+#undef GVV_RASTER_ATTR
     attrSet = true;
   }
+#define GVV_RASTER_LAUNCH(TS, RC, NTH) raster_kernel<TS, RC, NTH><<<gridT, NTH, raster_smem_bytes<TS, RC, NTH>(), st>>>(p)
   if (a.tile == 16) {
-    if (a.rayCache) raster_kernel<16, true><<<gridT, 256, raster_smem_bytes<16, true>(), st>>>(p);
-    else raster_kernel<16, false><<<gridT, 256, raster_smem_bytes<16, false>(), st>>>(p);
+    if (a.rayCache) GVV_RASTER_LAUNCH(16, true, 256);
+    else if (a.ctaThreads == 128) GVV_RASTER_LAUNCH(16, false, 128);
+    else GVV_RASTER_LAUNCH(16, false, 256);
   } else {
-    if (a.rayCache) raster_kernel<32, true><<<gridT, 256, raster_smem_bytes<32, true>(), st>>>(p);
-    else raster_kernel<32, false><<<gridT, 256, raster_smem_bytes<32, false>(), st>>>(p);
+    if (a.rayCache) GVV_RASTER_LAUNCH(32, true, 256);
+    else if (a.ctaThreads == 128) GVV_RASTER_LAUNCH(32, false, 128);
+    else GVV_RASTER_LAUNCH(32, false, 256);
   }
+#undef GVV_RASTER_LAUNCH
   tm->end(st);
   ++launches;
   return launch_ok() ? launches : -1;
