@@ -54,6 +54,9 @@ face_normal_kernel(const float* __restrict__ vertex_pos, const int4* __restrict_
   fnorm4[(size_t)b * F + f] = make_float4(fn.x, fn.y, fn.z, 0.f);
 }
 
+// one thread per (view, vertex): the C cameras of a batch element run in parallel (the CSR gather of
+// the normal is repeated per camera -- six 16-byte loads -- which is cheaper than serialising the
+// C projections with their IEEE divides in one thread)
 __global__ void __launch_bounds__(128)
 vertex_kernel(const float* __restrict__ vertex_pos, const float* __restrict__ vertex_color,
               const float4* __restrict__ fnorm4, const int* __restrict__ vfOffsets, const int* __restrict__ vfList,
@@ -62,17 +65,11 @@ vertex_kernel(const float* __restrict__ vertex_pos, const float* __restrict__ ve
               float4* __restrict__ vnorm4, float4* __restrict__ vcol4, float* __restrict__ vertex_normal_out,
               int N, int F, int C) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
-  if (blockIdx.x == 0)   // consumed by bin_count_kernel (next launch)
-    for (int c = threadIdx.x; c < C; c += blockDim.x) bigCount[b * C + c] = 0;
+  const int view = blockIdx.y, b = view / C, c = view - b * C;
+  if (blockIdx.x == 0 && threadIdx.x == 0) bigCount[view] = 0;   // consumed by bin_count_kernel (next launch)
   if (n >= N) return;
   const float* pos = vertex_pos + (size_t)b * N * 3;
   const F3 p = ld3(pos, n);
-  vscaled[(size_t)b * N + n] = make_float4(__fdiv_rn(p.x, 1000.f), __fdiv_rn(p.y, 1000.f), __fdiv_rn(p.z, 1000.f), 0.f);
-  if (vertex_color) {
-    const F3 col = ld3(vertex_color + (size_t)b * N * 3, n);
-    vcol4[(size_t)b * N + n] = make_float4(col.x, col.y, col.z, 0.f);
-  }
   // vertex normal = sum of incident face normals in ascending face order (ref :148-174); the
   // reference leaves vertices without faces uninitialised, we define them as 0.
   F3 nrm = mk3(0.f, 0.f, 0.f);
@@ -83,12 +80,16 @@ vertex_kernel(const float* __restrict__ vertex_pos, const float* __restrict__ ve
     if (i == beg) nrm = mk3(fn.x, fn.y, fn.z);
     else nrm = mk3(__fadd_rn(nrm.x, fn.x), __fadd_rn(nrm.y, fn.y), __fadd_rn(nrm.z, fn.z));
   }
-  vnorm4[(size_t)b * N + n] = make_float4(nrm.x, nrm.y, nrm.z, 0.f);
-  for (int c = 0; c < C; ++c) {
-    const int view = b * C + c;
-    float* vn = vertex_normal_out + ((size_t)view * N + n) * 3;
-    vn[0] = nrm.x; vn[1] = nrm.y; vn[2] = nrm.z;
-    proj[(size_t)view * N + n] = project_exact(intr + view * 9, extr + view * 12, p.x, p.y, p.z);
+  float* vn = vertex_normal_out + ((size_t)view * N + n) * 3;
+  vn[0] = nrm.x; vn[1] = nrm.y; vn[2] = nrm.z;
+  proj[(size_t)view * N + n] = project_exact(intr + view * 9, extr + view * 12, p.x, p.y, p.z);
+  if (c == 0) {
+    vscaled[(size_t)b * N + n] = make_float4(__fdiv_rn(p.x, 1000.f), __fdiv_rn(p.y, 1000.f), __fdiv_rn(p.z, 1000.f), 0.f);
+    vnorm4[(size_t)b * N + n] = make_float4(nrm.x, nrm.y, nrm.z, 0.f);
+    if (vertex_color) {
+      const F3 col = ld3(vertex_color + (size_t)b * N * 3, n);
+      vcol4[(size_t)b * N + n] = make_float4(col.x, col.y, col.z, 0.f);
+    }
   }
 }
 
@@ -110,6 +111,10 @@ __device__ __forceinline__ TileRange tile_range(const int4* __restrict__ faces4,
   return r;
 }
 
+// Each block bins kBinFacesPerThread * 256 consecutive triangles of one view, so that clearing and
+// flushing the per-block tile histogram (nT entries) is amortised over 1024 triangles.
+constexpr int kBinFacesPerThread = 4;
+
 template <bool SMEM_HIST>
 __global__ void __launch_bounds__(256)
 bin_count_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj, int* __restrict__ tileCount,
@@ -117,12 +122,14 @@ bin_count_kernel(const int4* __restrict__ faces4, const float4* __restrict__ pro
                  int tilesX, int nT) {
   extern __shared__ int hist[];
   const int view = blockIdx.y;
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (SMEM_HIST) {
     for (int i = threadIdx.x; i < nT; i += blockDim.x) hist[i] = 0;
     __syncthreads();
   }
-  if (f < F) {
+#pragma unroll
+  for (int k = 0; k < kBinFacesPerThread; ++k) {
+    const int f = (blockIdx.x * kBinFacesPerThread + k) * blockDim.x + threadIdx.x;
+    if (f >= F) continue;
     const TileRange r = tile_range(faces4, proj + (size_t)view * N, f, W, H, tileShift);
     if (r.n > kMaxSmallTiles) {
       const int slot = atomicAdd(bigCount + view, 1);
@@ -211,19 +218,26 @@ bin_fill_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj
   int* hist = sm;
   int* base = sm + nT;
   const int view = blockIdx.y;
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  TileRange r; r.n = 0; r.tx0 = r.ty0 = 0; r.tx1 = r.ty1 = -1;
-  if (f < F) r = tile_range(faces4, proj + (size_t)view * N, f, W, H, tileShift);
-  const bool small = r.n > 0 && r.n <= kMaxSmallTiles;
+  TileRange r[kBinFacesPerThread];
+  int fid[kBinFacesPerThread];
+#pragma unroll
+  for (int k = 0; k < kBinFacesPerThread; ++k) {
+    fid[k] = (blockIdx.x * kBinFacesPerThread + k) * blockDim.x + threadIdx.x;
+    r[k].n = 0; r[k].tx0 = r[k].ty0 = 0; r[k].tx1 = r[k].ty1 = -1;
+    if (fid[k] < F) r[k] = tile_range(faces4, proj + (size_t)view * N, fid[k], W, H, tileShift);
+    if (r[k].n > kMaxSmallTiles) r[k].n = 0;      // big triangles live in the big list (bin_count_kernel)
+  }
   int* viewBins = bins + (size_t)view * F * kMaxSmallTiles;
   const int* off = tileOffset + (size_t)view * nT;
   int* cur = tileCursor + (size_t)view * nT;
   if (SMEM_HIST) {
     for (int i = threadIdx.x; i < nT; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    if (small)
-      for (int ty = r.ty0; ty <= r.ty1; ++ty)
-        for (int tx = r.tx0; tx <= r.tx1; ++tx) atomicAdd(&hist[ty * tilesX + tx], 1);
+#pragma unroll
+    for (int k = 0; k < kBinFacesPerThread; ++k)
+      if (r[k].n > 0)
+        for (int ty = r[k].ty0; ty <= r[k].ty1; ++ty)
+          for (int tx = r[k].tx0; tx <= r[k].tx1; ++tx) atomicAdd(&hist[ty * tilesX + tx], 1);
     __syncthreads();
     // one global reservation per tile this block touches
     for (int i = threadIdx.x; i < nT; i += blockDim.x) {
@@ -231,18 +245,23 @@ bin_fill_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj
       if (c) { base[i] = off[i] + atomicAdd(cur + i, c); hist[i] = 0; }
     }
     __syncthreads();
-    if (small)
-      for (int ty = r.ty0; ty <= r.ty1; ++ty)
-        for (int tx = r.tx0; tx <= r.tx1; ++tx) {
-          const int t = ty * tilesX + tx;
-          viewBins[base[t] + atomicAdd(&hist[t], 1)] = f;
-        }
-  } else if (small) {
-    for (int ty = r.ty0; ty <= r.ty1; ++ty)
-      for (int tx = r.tx0; tx <= r.tx1; ++tx) {
-        const int t = ty * tilesX + tx;
-        viewBins[off[t] + atomicAdd(cur + t, 1)] = f;
-      }
+#pragma unroll
+    for (int k = 0; k < kBinFacesPerThread; ++k)
+      if (r[k].n > 0)
+        for (int ty = r[k].ty0; ty <= r[k].ty1; ++ty)
+          for (int tx = r[k].tx0; tx <= r[k].tx1; ++tx) {
+            const int t = ty * tilesX + tx;
+            viewBins[base[t] + atomicAdd(&hist[t], 1)] = fid[k];
+          }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kBinFacesPerThread; ++k)
+      if (r[k].n > 0)
+        for (int ty = r[k].ty0; ty <= r[k].ty1; ++ty)
+          for (int tx = r[k].tx0; tx <= r[k].tx1; ++tx) {
+            const int t = ty * tilesX + tx;
+            viewBins[off[t] + atomicAdd(cur + t, 1)] = fid[k];
+          }
   }
 }
 
@@ -367,22 +386,42 @@ __device__ __forceinline__ float sh_eval(const float* __restrict__ sh, F3 n) {
   return s;
 }
 
+// z-tile entry: the 64-bit (depth|id) key plus the winner's barycentrics, updated together by ONE
+// 128-bit shared-memory compare-and-swap (ATOMS.CAS.128, sm_90+), so that the resolve stage reads
+// (a,b) instead of re-running triangle setup and the exact test for every covered pixel.
+struct __align__(16) ZEntry { unsigned long long key; float a, b; };
+
+__device__ __forceinline__ ZEntry cas128_shared(ZEntry* addr, ZEntry cmp, ZEntry val) {
+  ZEntry old;
+  unsigned long long oab;
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(addr);
+  const unsigned long long cab = ((unsigned long long)__float_as_uint(cmp.b) << 32) | __float_as_uint(cmp.a);
+  const unsigned long long vab = ((unsigned long long)__float_as_uint(val.b) << 32) | __float_as_uint(val.a);
+  asm volatile("{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%3, %4};\n\tmov.b128 v, {%5, %6};\n\t"
+               "atom.shared.cas.b128 o, [%2], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
+               : "=l"(old.key), "=l"(oab) : "r"(sa), "l"(cmp.key), "l"(cab), "l"(val.key), "l"(vab) : "memory");
+  old.a = __uint_as_float((unsigned)oab);
+  old.b = __uint_as_float((unsigned)(oab >> 32));
+  return old;
+}
+
 // Shared-memory plan of raster_kernel (dynamic, carved by hand):
-//   zt[TS*TS] u64 | rayx,rayy,rayz[TS*TS] f32 | per warp: rec[32], erec[32], startArr[68], spanStart[68], spanInfo[32]
-constexpr int kWarpSmemBytes = 32 * (int)sizeof(TriRec) + 32 * (int)sizeof(EdgeRec) + (68 + 68 + 32) * 4;
+//   zt[TS*TS] ZEntry | rayx,rayy,rayz[TS*TS] f32 (RC only) | per warp: rec[kBatch], erec[kBatch], startArr[60], spanStart[68], spanInfo[32]
+constexpr int kBatch = 24;   // triangles a warp sets up at a time
+constexpr int kWarpSmemBytes = kBatch * (int)sizeof(TriRec) + kBatch * (int)sizeof(EdgeRec) + (60 + 68 + 32) * 4;
 // RC = per-pixel ray cache in shared memory (3 CTAs/SM) or rays recomputed per use (4 CTAs/SM, <= 64 registers)
 // NTH = threads per tile CTA (256 or 128)
 template <int TS, bool RC, int NTH>
-constexpr int raster_smem_bytes() { return TS * TS * (8 + (RC ? 12 : 0)) + (NTH / 32) * kWarpSmemBytes; }
+constexpr int raster_smem_bytes() { return TS * TS * (16 + (RC ? 12 : 0)) + (NTH / 32) * kWarpSmemBytes; }
 
 template <int TS, bool RC, int NTH>
 __global__ void __launch_bounds__(NTH, (RC ? 3 : 4) * (256 / NTH))
 raster_kernel(const RasterParams p) {
   constexpr int NPIX = TS * TS;
-  constexpr int ZRAY = NPIX * (8 + (RC ? 12 : 0));
+  constexpr int ZRAY = NPIX * (16 + (RC ? 12 : 0));
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  unsigned long long* zt = reinterpret_cast<unsigned long long*>(smemRaw);
-  float* rayx = reinterpret_cast<float*>(smemRaw + NPIX * 8);
+  ZEntry* zt = reinterpret_cast<ZEntry*>(smemRaw);
+  float* rayx = reinterpret_cast<float*>(smemRaw + NPIX * 16);
   float* rayy = rayx + NPIX;
   float* rayz = rayy + NPIX;
   __shared__ float shc[27];
@@ -422,7 +461,7 @@ raster_kernel(const RasterParams p) {
 
   // z-tile clear + per-pixel ray cache (the ray depends on pixel and camera only)
   for (int q = tid; q < NPIX; q += NTH) {
-    zt[q] = kEmptyKey;
+    { ZEntry e; e.key = kEmptyKey; e.a = 0.f; e.b = 0.f; zt[q] = e; }
     const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
     if (RC) {
       const F3 rd = ray_dir_exact(cam.Pinv, cam.ro, __fadd_rn((float)x, 0.5f), __fadd_rn((float)y, 0.5f));
@@ -440,12 +479,12 @@ raster_kernel(const RasterParams p) {
   // rasterises them; no block-wide barrier until all batches are done. ----
   unsigned char* wbase = smemRaw + ZRAY + warp * kWarpSmemBytes;
   TriRec* rec = reinterpret_cast<TriRec*>(wbase);
-  EdgeRec* erec = reinterpret_cast<EdgeRec*>(wbase + 32 * sizeof(TriRec));
-  int* startArr = reinterpret_cast<int*>(wbase + 32 * (sizeof(TriRec) + sizeof(EdgeRec)));
-  int* mySpanStart = startArr + 68;
+  EdgeRec* erec = reinterpret_cast<EdgeRec*>(wbase + kBatch * sizeof(TriRec));
+  int* startArr = reinterpret_cast<int*>(wbase + kBatch * (sizeof(TriRec) + sizeof(EdgeRec)));
+  int* mySpanStart = startArr + 60;
   int* mySpanInfo = mySpanStart + 68;
 
-  // exact test + 64-bit atomicMin for one (triangle k of the batch, tile pixel q) pair
+  // exact test + atomicMin into the z-tile for one (triangle k of the batch, tile pixel q) pair
   auto exact_pair = [&](int k, int q) {
     const float4* rp = reinterpret_cast<const float4*>(&rec[k]);
     const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3];
@@ -457,18 +496,19 @@ raster_kernel(const RasterParams p) {
     float a, bq, c;
     if (hit_exact(ts, ros, rd, a, bq, c)) {
       const int depth = depth_key_exact(a, bq, c, r3.z, r3.w, __int_as_float(r4.x));
-      const unsigned long long key = pack_key(depth, r4.y);
-      unsigned long long cur = zt[q];
-      while (key < cur) {                     // 64-bit atomicMin on the shared z-tile
-        const unsigned long long old = atomicCAS(&zt[q], cur, key);
-        if (old == cur) break;
+      ZEntry nv;
+      nv.key = pack_key(depth, r4.y); nv.a = a; nv.b = bq;
+      ZEntry cur = zt[q];
+      while (nv.key < cur.key) {              // atomicMin on the 64-bit key; (a,b) ride along in the same 128-bit CAS
+        const ZEntry old = cas128_shared(&zt[q], cur, nv);
+        if (old.key == cur.key && __float_as_uint(old.a) == __float_as_uint(cur.a) && __float_as_uint(old.b) == __float_as_uint(cur.b)) break;
         cur = old;
       }
     }
   };
 
   const int cntAll = cntSmall + cntBig;
-  const int G = min(32, max(1, (cntAll + p.batchDiv - 1) / p.batchDiv));   // triangles per batch: a short bin is spread over the warps
+  const int G = min(kBatch, max(1, (cntAll + p.batchDiv - 1) / p.batchDiv));   // triangles per batch: a short bin is spread over the warps
   const int* smallList = p.bins + (size_t)view * p.F * kMaxSmallTiles + p.tileOffset[tidx];
   const int* bigList = p.bigList + (size_t)view * p.F;
   const float4* vs = p.vscaled + (size_t)b * p.N;
@@ -593,16 +633,16 @@ raster_kernel(const RasterParams p) {
     const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
     if (x >= p.W || y >= p.H) continue;
     const size_t pix = pixBase + (size_t)y * p.W + x;
-    const unsigned long long key = zt[q];
+    const ZEntry ze = zt[q];
+    const unsigned long long key = ze.key;
     int faceId = -1;
     float a = 0.f, bq = 0.f, cr = 0.f, cg = 1.f, cb = 0.f;
     if (key != kEmptyKey) {
       faceId = (int)(unsigned)(key & 0xffffffffull);
       const int4 fc = __ldg(p.faces4 + faceId);
-      float z0, z1, z2, c;
-      const TriSetup ts = load_setup(p, b, view, fc, ros, z0, z1, z2, nullptr);
+      a = ze.a; bq = ze.b;                               // the winner's barycentrics, stored with its key
+      const float c = __fsub_rn(__fsub_rn(1.f, a), bq);  // c = 1 - a - b (RendererUtil.h:125)
       const F3 rd = ray_of(q);
-      hit_exact(ts, ros, rd, a, bq, c);   // same arithmetic as the rasterising pass => same (a,b,c)
       const float4 n0 = __ldg(vn + fc.x), n1 = __ldg(vn + fc.y), n2 = __ldg(vn + fc.z);
       F3 nr = mk3(interp3(a, bq, c, n0.x, n1.x, n2.x), interp3(a, bq, c, n0.y, n1.y, n2.y), interp3(a, bq, c, n0.z, n1.z, n2.z));
       const float len = __fsqrt_rn(dot3x(nr, nr));
@@ -685,7 +725,7 @@ int launch_camera(const float* extr, const float* intr, CamRec* cams, int* bigCo
 
 int launch_vertex(const FwdArgs& a, cudaStream_t st) {
   if (a.F > 0) face_normal_kernel<<<dim3((a.F + 255) / 256, a.B), 256, 0, st>>>(a.vertex_pos, a.faces4, a.s.fnorm4, a.N, a.F);
-  vertex_kernel<<<dim3((a.N + 127) / 128, a.B), 128, 0, st>>>(a.vertex_pos, a.vertex_color, a.s.fnorm4, a.vfOffsets, a.vfList,
+  vertex_kernel<<<dim3((a.N + 127) / 128, a.B * a.C), 128, 0, st>>>(a.vertex_pos, a.vertex_color, a.s.fnorm4, a.vfOffsets, a.vfList,
                                                              a.extrinsics, a.intrinsics, a.s.bigCount,
                                                              a.s.proj, a.s.vscaled, a.s.vnorm4, a.s.vcol4,
                                                              a.vertex_normal, a.N, a.F, a.C);
@@ -699,7 +739,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   launches += launch_vertex(a, st);   // face normals + per-vertex work
   tm->end(st);
   const int tileShift = a.tile == 32 ? 5 : 4;
-  const dim3 gridF((a.F + 255) / 256, V);
+  const dim3 gridF((a.F + 256 * kBinFacesPerThread - 1) / (256 * kBinFacesPerThread), V);
   tm->begin(K_BIN_COUNT, st);
   if (a.nT <= kSmemHistTiles) {
     bin_count_kernel<true><<<gridF, 256, a.nT * sizeof(int), st>>>(a.faces4, a.s.proj, a.s.tileCount, a.s.bigCount, a.s.bigList,
