@@ -117,7 +117,9 @@ __device__ __forceinline__ TriSetup tri_setup_exact(F3 v0s, F3 v1s, F3 v2s, F3 r
 // Pixel part of rayTriangleIntersect + uv2barycentric (RendererUtil.h:46-127) + the inside test of
 // CUDABasedRasterization.cu:243.  Returns true iff the reference would call atomicMin for this pair;
 // a,b,c are then the reference's barycentrics (bit-exact).
-__device__ __forceinline__ bool hit_exact(const TriSetup& t, F3 ros, F3 rd, float& a, float& b, float& c) {
+// skip_rest: the caller already knows this pair cannot win the depth test (conservative early-z, see
+// raster_kernel); the remaining divides are then not spent.  It never changes a result that is used.
+__device__ __forceinline__ bool hit_exact(const TriSetup& t, F3 ros, F3 rd, float& a, float& b, float& c, bool skip_rest = false) {
   const float nd = dot3x(rd, t.N);
   if (fabsf(nd) < 0.0000001f) return false;
   const float tt = __fdiv_rn(t.num, nd);
@@ -129,6 +131,7 @@ __device__ __forceinline__ bool hit_exact(const TriSetup& t, F3 ros, F3 rd, floa
   const float an = dot3x(t.N, cross3x(sub3(t.v2, t.v1), sub3(P, t.v1)));
   const float bn = dot3x(t.N, cross3x(sub3(t.v0, t.v2), sub3(P, t.v2)));
   if (e0n < 0.f || an < 0.f || bn < 0.f) return false;
+  if (skip_rest) return false;
   a = __fdiv_rn(an, t.den);
   b = __fdiv_rn(bn, t.den);
   c = __fsub_rn(__fsub_rn(1.f, a), b);

@@ -494,11 +494,15 @@ raster_kernel(const RasterParams p) {
     ts.N = mk3(r2.y, r2.z, r2.w); ts.num = r3.x; ts.den = r3.y;
     const F3 rd = ray_of(q);
     float a, bq, c;
-    if (hit_exact(ts, ros, rd, a, bq, c)) {
+    // conservative early-z: r4.z is a lower bound of every depth key this triangle can produce
+    // (0.99 * min vertex depth, only for triangles with zmax <= 2 zmin); if even that is behind the
+    // pixel's current winner the pair cannot win (ties have equal keys and are never skipped)
+    ZEntry cur = zt[q];
+    const bool behind = (unsigned)(r4.z ^ 0x80000000) > (unsigned)(cur.key >> 32);
+    if (hit_exact(ts, ros, rd, a, bq, c, behind)) {
       const int depth = depth_key_exact(a, bq, c, r3.z, r3.w, __int_as_float(r4.x));
       ZEntry nv;
       nv.key = pack_key(depth, r4.y); nv.a = a; nv.b = bq;
-      ZEntry cur = zt[q];
       while (nv.key < cur.key) {              // atomicMin on the 64-bit key; (a,b) ride along in the same 128-bit CAS
         const ZEntry old = cas128_shared(&zt[q], cur, nv);
         if (old.key == cur.key && __float_as_uint(old.a) == __float_as_uint(cur.a) && __float_as_uint(old.b) == __float_as_uint(cur.b)) break;
@@ -539,7 +543,11 @@ raster_kernel(const RasterParams p) {
         mine.v2x = ts.v2.x; mine.v2y = ts.v2.y; mine.v2z = ts.v2.z;
         mine.Nx = ts.N.x; mine.Ny = ts.N.y; mine.Nz = ts.N.z;
         mine.num = ts.num; mine.den = ts.den; mine.z0 = p0.z; mine.z1 = p1.z; mine.z2 = p2.z;
-        mine.face = f; mine.pad0 = 0; mine.pad1 = 0;
+        mine.face = f; mine.pad1 = 0;
+        {   // z = 1/(a/z0+b/z1+c/z2) with a,b,c in [-0.001,1.001] stays above zmin*(1-0.003*zmax/zmin) >= 0.99*zmin for zmax <= 2 zmin
+          const float zmin = fminf(p0.z, fminf(p1.z, p2.z)), zmax = fmaxf(p0.z, fmaxf(p1.z, p2.z));
+          mine.pad0 = (zmin > 0.f && zmax <= 2.f * zmin) ? __float2int_rd(zmin * 9900.f) - 1 : (int)0x80000000;
+        }
         edge_setup(p0, p1, p2, (float)tileX0, (float)tileY0, p.cullMargin, em);
         em.geom = (cx0 - tileX0) | ((cy0 - tileY0) << 8) | (w << 16);
         em.pad0 = 0; em.pad1 = 0;
