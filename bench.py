@@ -29,6 +29,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_OUT = sys.stdout
 BASE = json.load(open(os.path.join(ROOT, "BASELINE.json"))) if os.path.exists(os.path.join(ROOT, "BASELINE.json")) else {}
 METRIC = BASE.get("metric", "views/sec fwd+bwd at 1024^2, 70k tris")
 UNIT = "views/s"
@@ -111,6 +112,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner must not land on stdout next to the JSON line
         dist.init_process_group("nccl", device_id=dev)
     sc = make_inputs(rank)
     N, C, W, H = sc["num_vertices"], sc["num_cameras"], sc["width"], sc["height"]
@@ -262,7 +264,7 @@ def run_ours(args, rank, world, local_rank):
                            "l2": "no explicit flush: a step streams ~300 MB of buffers (192 MB outputs + 100 MB render gradient) through a 126 MB L2",
                            "collective": "none" if world == 1 else "1 NCCL all-reduce/step of shared SH + colour gradients (%d B)" % ((C * 27 + N * 3) * 4)},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -346,10 +348,16 @@ def run_reference(args, rank, world, local_rank):
         cb["sample"] += " (oracle/_ref not available: CPU port timed instead)"
         line.update(value=cb["value"], ms_per_step=round(1e3 * C / cb["value"], 2), cpu_baseline=cb,
                     e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 def main():
+    # Only the JSON line may reach stdout: libraries (NCCL's version banner, for one) print there too,
+    # so fd 1 is pointed at stderr for the whole run and the result goes to a private copy of it.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
