@@ -357,7 +357,7 @@ struct RasterParams {
   int* tileCount; int* tileCursor; const int* tileOffset; const int* tileOrder; const int* bigCount; const int* bigList; const int* bins;
   const float* texture; const float* texcoords; const float* sh_coeff;
   float* bary; int32_t* face; float* render;
-  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, V, batchDiv;
+  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, V, batchDiv, interleave;
   float cullMargin;
 };
 
@@ -513,16 +513,20 @@ raster_kernel(const RasterParams p) {
 
   const int cntAll = cntSmall + cntBig;
   const int G = min(kBatch, max(1, (cntAll + p.batchDiv - 1) / p.batchDiv));   // triangles per batch: a short bin is spread over the warps
+  const int nBatches = (cntAll + G - 1) / G;
   const int* smallList = p.bins + (size_t)view * p.F * kMaxSmallTiles + p.tileOffset[tidx];
   const int* bigList = p.bigList + (size_t)view * p.F;
   const float4* vs = p.vscaled + (size_t)b * p.N;
   const float4* pj = p.proj + (size_t)view * p.N;
   for (;;) {
+    // batch j takes the bin entries j, j + nBatches, j + 2 nBatches, ... (interleave = 1, the default):
+    // every warp gets a sample of the whole bin instead of one spatially coherent chunk, which evens
+    // out the batches and shortens the wait at the barrier before the resolve stage
     int base = 0;
-    if (lane == 0) base = atomicAdd(&nextBatch, G);
+    if (lane == 0) base = atomicAdd(&nextBatch, p.interleave ? 1 : G);
     base = __shfl_sync(FULL_MASK, base, 0);
-    if (base >= cntAll) break;
-    const int i = base + lane;
+    if (base >= (p.interleave ? nBatches : cntAll)) break;
+    const int i = p.interleave ? base + lane * nBatches : base + lane;
     int n = 0;
     TriRec mine;
     EdgeRec em;
@@ -779,7 +783,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   p.texture = a.texture; p.texcoords = a.texcoords; p.sh_coeff = a.sh_coeff;
   p.bary = a.bary; p.face = a.face; p.render = a.render;
   p.C = a.C; p.N = a.N; p.F = a.F; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
-  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv;
+  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv; p.interleave = a.interleave;
   const dim3 gridT((unsigned)a.nT * (unsigned)V);
   tm->begin(K_RASTER, st);
   static bool attrSet = false;
