@@ -192,6 +192,7 @@ extern "C" int gvv_set_option(gvv_handle h, const char* key, int32_t value) {
   }
   if (!strcmp(key, "batch_div")) { if (value < 1) return fail(GVV_EINVAL, "batch_div must be >= 1"); h->batchDiv = value; return GVV_OK; }
   if (!strcmp(key, "cta_threads")) { if (value != 128 && value != 256) return fail(GVV_EINVAL, "cta_threads must be 128 or 256"); h->ctaThreads = value; return GVV_OK; }
+  if (!strcmp(key, "hiz")) { h->hiz = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "interleave")) { h->interleave = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "ray_cache")) { h->rayCache = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "time_kernels")) {
@@ -234,7 +235,7 @@ extern "C" int gvv_forward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
   FwdArgs a;
   a.B = B; a.C = h->C; a.N = h->N; a.F = h->F; a.W = h->W; a.H = h->H; a.texH = texH; a.texW = texW;
   a.albedo = h->albedo; a.shading = h->shading;
-  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin; a.rayCache = h->rayCache; a.batchDiv = h->batchDiv; a.ctaThreads = h->ctaThreads; a.interleave = h->interleave;
+  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin; a.rayCache = h->rayCache; a.batchDiv = h->batchDiv; a.ctaThreads = h->ctaThreads; a.interleave = h->interleave; a.hiz = h->hiz;
   a.vertex_pos = vertex_pos; a.vertex_color = vertex_color; a.texture = texture; a.sh_coeff = sh_coeff;
   a.extrinsics = extrinsics; a.intrinsics = intrinsics; a.texcoords = h->texcoords;
   a.faces4 = h->faces4; a.vfOffsets = h->vfOffsets; a.vfList = h->vfList;

@@ -357,7 +357,7 @@ struct RasterParams {
   int* tileCount; int* tileCursor; const int* tileOffset; const int* tileOrder; const int* bigCount; const int* bigList; const int* bins;
   const float* texture; const float* texcoords; const float* sh_coeff;
   float* bary; int32_t* face; float* render;
-  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, V, batchDiv, interleave;
+  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, V, batchDiv, interleave, hiz;
   float cullMargin;
 };
 
@@ -405,6 +405,14 @@ __device__ __forceinline__ ZEntry cas128_shared(ZEntry* addr, ZEntry cmp, ZEntry
   return old;
 }
 
+// Lower bound of every depth key a triangle can produce: z = 1/(a/z0+b/z1+c/z2) with a,b,c in
+// [-0.001,1.001] stays above zmin*(1 - 0.003*zmax/zmin) >= 0.99*zmin when zmax <= 2 zmin; INT_MIN
+// (= no bound) otherwise.  Used only to SKIP work that provably cannot win the depth test.
+__device__ __forceinline__ int key_lower_bound(float z0, float z1, float z2) {
+  const float zmin = fminf(z0, fminf(z1, z2)), zmax = fmaxf(z0, fmaxf(z1, z2));
+  return (zmin > 0.f && zmax <= 2.f * zmin) ? __float2int_rd(zmin * 9900.f) - 1 : (int)0x80000000;
+}
+
 // Shared-memory plan of raster_kernel (dynamic, carved by hand):
 //   zt[TS*TS] ZEntry | rayx,rayy,rayz[TS*TS] f32 (RC only) | per warp: rec[kBatch], erec[kBatch], startArr[60], spanStart[68], spanInfo[32]
 constexpr int kBatch = 24;   // triangles a warp sets up at a time
@@ -427,6 +435,8 @@ raster_kernel(const RasterParams p) {
   __shared__ float shc[27];
   __shared__ CamRec cam;
   __shared__ int nextBatch;
+  __shared__ int sMinK, sMaxK, sLate;
+  __shared__ unsigned sZmax;
 
   // 1-D grid, view fastest: the heaviest tiles of every view are scheduled first
   const int view = blockIdx.x % p.V;
@@ -455,7 +465,7 @@ raster_kernel(const RasterParams p) {
 
   if (tid < 64) reinterpret_cast<float*>(&cam)[tid] = reinterpret_cast<const float*>(p.cams + view)[tid];
   if (tid >= 64 && tid < 64 + 27) shc[tid - 64] = p.sh_coeff[(size_t)view * 27 + (tid - 64)];
-  if (tid == 96) nextBatch = 0;
+  if (tid == 96) { nextBatch = 0; sMinK = 0x7fffffff; sMaxK = (int)0x80000000; sLate = 0; sZmax = 0u; }
   __syncthreads();
   const F3 ros = mk3(cam.ros[0], cam.ros[1], cam.ros[2]);
 
@@ -518,6 +528,41 @@ raster_kernel(const RasterParams p) {
   const int* bigList = p.bigList + (size_t)view * p.F;
   const float4* vs = p.vscaled + (size_t)b * p.N;
   const float4* pj = p.proj + (size_t)view * p.N;
+
+  // ---- hierarchical z.  The bin is rasterised in two passes: first the triangles whose depth-key
+  // lower bound lies in the nearer half of the bin's range, then the rest -- and a triangle of the
+  // second pass whose lower bound is behind EVERY pixel of the (by then fully covered) z-tile is
+  // dropped before any of its rows is touched.  Keys only ever decrease, so such a triangle can win
+  // no pixel: the result is bit-identical (hiz = 0 rasterises everything in one pass). ----
+  int thr = 0x7fffffff;                               // pass 0 takes lower bounds <= thr
+  if (p.hiz && cntAll >= 64) {
+    int mn = 0x7fffffff, mx = (int)0x80000000;
+    for (int i = tid; i < cntAll; i += NTH) {
+      const int4 fc = __ldg(p.faces4 + __ldg(i < cntSmall ? smallList + i : bigList + (i - cntSmall)));
+      const int k = key_lower_bound(__ldg(pj + fc.x).z, __ldg(pj + fc.y).z, __ldg(pj + fc.z).z);
+      if (k != (int)0x80000000) { mn = min(mn, k); mx = max(mx, k); }
+    }
+    mn = __reduce_min_sync(FULL_MASK, mn); mx = __reduce_max_sync(FULL_MASK, mx);
+    if (lane == 0) { atomicMin(&sMinK, mn); atomicMax(&sMaxK, mx); }
+    __syncthreads();
+    if (sMaxK > sMinK) thr = sMinK + ((sMaxK - sMinK) >> 1);
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+  unsigned zmaxBits = 0xffffffffu;                    // pass 1: farthest current winner of the tile (0xffffffff if a pixel is still empty)
+  if (pass == 1) {
+    __syncthreads();                                  // pass 0 complete
+    if (sLate == 0) break;                            // nothing was deferred
+    unsigned m = 0u;
+    for (int q = tid; q < NPIX; q += NTH) {
+      const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
+      if (x < p.W && y < p.H) m = max(m, (unsigned)(zt[q].key >> 32));
+    }
+    m = __reduce_max_sync(FULL_MASK, m);
+    if (lane == 0) atomicMax(&sZmax, m);
+    if (tid == 0) nextBatch = 0;
+    __syncthreads();
+    zmaxBits = sZmax;
+  }
   for (;;) {
     // batch j takes the bin entries j, j + nBatches, j + 2 nBatches, ... (interleave = 1, the default):
     // every warp gets a sample of the whole bin instead of one spatially coherent chunk, which evens
@@ -539,7 +584,12 @@ raster_kernel(const RasterParams p) {
       const int cx0 = max(bb.x, tileX0), cx1 = min(bb.z, tileX0 + TS - 1);
       const int cy0 = max(bb.y, tileY0), cy1 = min(bb.w, tileY0 + TS - 1);
       const int w = cx1 - cx0 + 1, h = cy1 - cy0 + 1;
-      if (w > 0 && h > 0) {
+      const int klb = key_lower_bound(p0.z, p1.z, p2.z);
+      const bool late = klb > thr;                     // belongs to pass 1
+      bool take = (w > 0 && h > 0) && (late == (pass == 1));
+      if (pass == 0 && late && w > 0 && h > 0) sLate = 1;          // benign race: every writer stores 1
+      if (pass == 1 && take && (unsigned)(klb ^ 0x80000000) > zmaxBits) take = false;   // behind the whole tile
+      if (take) {
         n = h;                 // work items are ROWS of the clipped bbox
         const TriSetup ts = tri_setup_exact(mk3(s0.x, s0.y, s0.z), mk3(s1.x, s1.y, s1.z), mk3(s2.x, s2.y, s2.z), ros);
         mine.v0x = ts.v0.x; mine.v0y = ts.v0.y; mine.v0z = ts.v0.z;
@@ -548,10 +598,7 @@ raster_kernel(const RasterParams p) {
         mine.Nx = ts.N.x; mine.Ny = ts.N.y; mine.Nz = ts.N.z;
         mine.num = ts.num; mine.den = ts.den; mine.z0 = p0.z; mine.z1 = p1.z; mine.z2 = p2.z;
         mine.face = f; mine.pad1 = 0;
-        {   // z = 1/(a/z0+b/z1+c/z2) with a,b,c in [-0.001,1.001] stays above zmin*(1-0.003*zmax/zmin) >= 0.99*zmin for zmax <= 2 zmin
-          const float zmin = fminf(p0.z, fminf(p1.z, p2.z)), zmax = fmaxf(p0.z, fmaxf(p1.z, p2.z));
-          mine.pad0 = (zmin > 0.f && zmax <= 2.f * zmin) ? __float2int_rd(zmin * 9900.f) - 1 : (int)0x80000000;
-        }
+        mine.pad0 = klb;       // also drives the per-pixel early-z in exact_pair
         edge_setup(p0, p1, p2, (float)tileX0, (float)tileY0, p.cullMargin, em);
         em.geom = (cx0 - tileX0) | ((cy0 - tileY0) << 8) | (w << 16);
         em.pad0 = 0; em.pad1 = 0;
@@ -635,6 +682,7 @@ raster_kernel(const RasterParams p) {
       __syncwarp();
     }
   }
+  }   // pass
   __syncthreads();
 
   // ---- resolve + shade + write (ref pass 2, :286-403) ----
@@ -783,7 +831,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   p.texture = a.texture; p.texcoords = a.texcoords; p.sh_coeff = a.sh_coeff;
   p.bary = a.bary; p.face = a.face; p.render = a.render;
   p.C = a.C; p.N = a.N; p.F = a.F; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
-  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv; p.interleave = a.interleave;
+  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv; p.interleave = a.interleave; p.hiz = a.hiz;
   const dim3 gridT((unsigned)a.nT * (unsigned)V);
   tm->begin(K_RASTER, st);
   static bool attrSet = false;

@@ -58,6 +58,7 @@ struct gvv_renderer {
   int F = 0, N = 0, C = 0, W = 0, H = 0;
   int albedo = 0, shading = 0, imgFilter = 1, texFilter = 1, computeNormalMap = 0;
   int tile = 32, tilesX = 0, tilesY = 0, nT = 0;
+  int hiz = 1;                // raster: two-pass hierarchical z (skips triangles behind the whole tile)
   int interleave = 1;         // raster: batch j takes bin entries j, j+nBatches, ... instead of a contiguous chunk
   int ctaThreads = 256;       // raster: threads per tile CTA (256 | 128)
   int batchDiv = 8;           // raster: a bin of n triangles is cut into batches of ceil(n / batchDiv) (<= 32) triangles
@@ -79,7 +80,7 @@ namespace gvv {
 
 struct FwdArgs {
   int B, C, N, F, W, H, texH, texW, albedo, shading;
-  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave;
+  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz;
   float cullMargin;
   const float *vertex_pos, *vertex_color, *texture, *sh_coeff, *extrinsics, *intrinsics;
   const float* texcoords;

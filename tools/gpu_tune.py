@@ -20,6 +20,7 @@ for cfg in configs:
     bd = cfg[3] if len(cfg) > 3 else 8
     nth = cfg[4] if len(cfg) > 4 else 256
     guided = cfg[5] if len(cfg) > 5 else 1
+    hiz = cfg[6] if len(cfg) > 6 else 1
     r = _native.NativeRenderer(sc["faces"], sc["texcoords"], N, C, W, H, "vertexColor", "shaded", 1, 1, False, dev)
     r.set_option("tile", tile)
     r.set_option("cull_margin_milli", margin)
@@ -27,6 +28,7 @@ for cfg in configs:
     r.set_option("batch_div", bd)
     r.set_option("cta_threads", nth)
     r.set_option("interleave", guided)
+    r.set_option("hiz", hiz)
     for _ in range(3):
         out = r.forward(*ins)
         r.backward(G, None, ins[0], ins[1], ins[2], ins[3], ins[4], out[3], out[0], out[1], ins[5], ins[6])
@@ -39,5 +41,5 @@ for cfg in configs:
         ref = (out[1].clone(), out[0].clone(), out[2].clone())
     same = bool(torch.equal(out[1], ref[0]) and torch.equal(out[0].view(torch.int32), ref[1].view(torch.int32))
                 and torch.equal(out[2].view(torch.int32), ref[2].view(torch.int32)))
-    print(json.dumps({"tile": tile, "margin_milli": margin, "ray_cache": rc, "batch_div": bd, "cta_threads": nth, "interleave": guided, "identical_to_unculled": same, "ms": kt}), flush=True)
+    print(json.dumps({"tile": tile, "margin_milli": margin, "ray_cache": rc, "batch_div": bd, "cta_threads": nth, "interleave": guided, "hiz": hiz, "identical_to_unculled": same, "ms": kt}), flush=True)
     r.close()
