@@ -39,8 +39,8 @@ static cudaError_t dmalloc(T** p, size_t count) {
 
 static void free_scratch(Scratch& s) {
   cudaFree(s.cams); cudaFree(s.proj); cudaFree(s.vscaled); cudaFree(s.fnorm4); cudaFree(s.vnorm4); cudaFree(s.vcol4);
-  cudaFree(s.tileCount); cudaFree(s.tileCursor); cudaFree(s.tileOffset); cudaFree(s.tileOrder); cudaFree(s.bigCount);
-  cudaFree(s.bigList); cudaFree(s.bins); cudaFree(s.gnorm); cudaFree(s.bpos4); cudaFree(s.bcol4); cudaFree(s.bnor4);
+  cudaFree(s.tileCount); cudaFree(s.tileCursor); cudaFree(s.tileOffset); cudaFree(s.tileOrder); cudaFree(s.tileDone); cudaFree(s.bigCount);
+  cudaFree(s.bigList); cudaFree(s.bins); cudaFree(s.gnorm); cudaFree(s.bpos4); cudaFree(s.bcol4); cudaFree(s.bnor4); cudaFree(s.ctaTrace);
   s = Scratch();
 }
 
@@ -70,7 +70,8 @@ static int ensure_scratch(gvv_renderer* h, int B, cudaStream_t st) {
   acc(dmalloc(&s.tileCount, (size_t)V * nT));
   acc(dmalloc(&s.tileCursor, (size_t)V * nT));
   acc(dmalloc(&s.tileOffset, (size_t)V * nT));
-  acc(dmalloc(&s.tileOrder, (size_t)V * nT));
+  acc(dmalloc(&s.tileOrder, (size_t)V * (nT + nT / 2)));
+  acc(dmalloc(&s.tileDone, (size_t)V * nT));
   acc(dmalloc(&s.bigCount, (size_t)V));
   acc(dmalloc(&s.bigList, (size_t)V * F));
   acc(dmalloc(&s.bins, (size_t)V * F * kMaxSmallTiles));
@@ -78,12 +79,14 @@ static int ensure_scratch(gvv_renderer* h, int B, cudaStream_t st) {
   acc(dmalloc(&s.bpos4, (size_t)B * N));
   acc(dmalloc(&s.bcol4, (size_t)B * N));
   acc(dmalloc(&s.bnor4, (size_t)V * N));
+  if (h->ctaTrace) acc(dmalloc(&s.ctaTrace, (size_t)V * (nT + nT / 2) * 4));
   if (e != cudaSuccess) {
     free_scratch(s);
     return fail(GVV_ENOMEM, "scratch allocation for %d views failed: %s", V, cudaGetErrorString(e));
   }
   CK(cudaMemsetAsync(s.tileCount, 0, (size_t)V * nT * sizeof(int), st));
   CK(cudaMemsetAsync(s.tileCursor, 0, (size_t)V * nT * sizeof(int), st));
+  CK(cudaMemsetAsync(s.tileDone, 0, (size_t)V * nT * sizeof(int), st));
   CK(cudaMemsetAsync(s.bigCount, 0, (size_t)V * sizeof(int), st));
   s.capViews = V;
   s.capBatch = B;
@@ -192,6 +195,9 @@ extern "C" int gvv_set_option(gvv_handle h, const char* key, int32_t value) {
   }
   if (!strcmp(key, "batch_div")) { if (value < 1) return fail(GVV_EINVAL, "batch_div must be >= 1"); h->batchDiv = value; return GVV_OK; }
   if (!strcmp(key, "cta_threads")) { if (value != 128 && value != 256) return fail(GVV_EINVAL, "cta_threads must be 128 or 256"); h->ctaThreads = value; return GVV_OK; }
+  if (!strcmp(key, "span_z")) { if (value < 0 || value > 2) return fail(GVV_EINVAL, "span_z must be 0 (off), 1 (both passes) or 2 (far pass only)"); h->spanZ = value; return GVV_OK; }
+  if (!strcmp(key, "cta_trace")) { cudaSetDevice(h->device); cudaDeviceSynchronize(); free_scratch(h->s); h->ctaTrace = value ? 1 : 0; return GVV_OK; }   // scratch is re-allocated by the next call
+  if (!strcmp(key, "split_unit")) { if (value < 0) return fail(GVV_EINVAL, "split_unit must be >= 0"); h->splitUnit = value; return GVV_OK; }
   if (!strcmp(key, "hiz")) { h->hiz = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "interleave")) { h->interleave = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "ray_cache")) { h->rayCache = value ? 1 : 0; return GVV_OK; }
@@ -235,7 +241,7 @@ extern "C" int gvv_forward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
   FwdArgs a;
   a.B = B; a.C = h->C; a.N = h->N; a.F = h->F; a.W = h->W; a.H = h->H; a.texH = texH; a.texW = texW;
   a.albedo = h->albedo; a.shading = h->shading;
-  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin; a.rayCache = h->rayCache; a.batchDiv = h->batchDiv; a.ctaThreads = h->ctaThreads; a.interleave = h->interleave; a.hiz = h->hiz;
+  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin; a.rayCache = h->rayCache; a.batchDiv = h->batchDiv; a.ctaThreads = h->ctaThreads; a.interleave = h->interleave; a.hiz = h->hiz; a.spanZ = h->spanZ; a.splitUnit = h->splitUnit;
   a.vertex_pos = vertex_pos; a.vertex_color = vertex_color; a.texture = texture; a.sh_coeff = sh_coeff;
   a.extrinsics = extrinsics; a.intrinsics = intrinsics; a.texcoords = h->texcoords;
   a.faces4 = h->faces4; a.vfOffsets = h->vfOffsets; a.vfList = h->vfList;
@@ -318,6 +324,7 @@ extern "C" int64_t gvv_debug_copy(gvv_handle h, int32_t which, void* dst, int64_
   int64_t bytes = 0;
   if (which == 0) { src = h->s.cams; bytes = (int64_t)h->s.capViews * sizeof(CamRec); }
   else if (which == 1) { src = h->s.proj; bytes = (int64_t)h->s.capViews * h->N * sizeof(float4); }
+  else if (which == 2) { src = h->s.ctaTrace; bytes = src ? (int64_t)h->s.capViews * (h->nT + h->nT / 2) * 4 * sizeof(unsigned long long) : 0; }
   else return -1;
   if (!src) return 0;
   const int64_t n = bytes < capacity ? bytes : capacity;

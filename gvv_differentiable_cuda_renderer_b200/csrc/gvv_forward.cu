@@ -151,16 +151,27 @@ bin_count_kernel(const int4* __restrict__ faces4, const float4* __restrict__ pro
   }
 }
 
-// exclusive scan of one view's tile histogram (one block per view) + the order in which the raster
-// CTAs visit the tiles: heaviest bins first (longest-processing-time-first keeps the silhouette
-// tiles, which hold ~10x the average work, out of the tail of the launch)
+// exclusive scan of one view's tile histogram (one block per view) + the raster work list of the view.
+// A work item is a horizontal STRIP of a tile: item = tile | strip << 20 | log2(K) << 24, the tile being cut
+// into K = 1, 2, 4 or 8 strips of TS/K rows, each rasterised by its own CTA (every strip scans the whole
+// bin of the tile and keeps the rows that fall into it).  Heavy bins are split so that the longest CTA
+// of the launch -- the critical path: a pole/silhouette tile holds ~15x the average bin -- shrinks; the
+// items are ordered heaviest first (counting sort by log2 of bin size / K: longest-processing-time-first).
+// The list has nItems = nT + nT/2 slots per view; unused slots hold -1.
+__device__ __forceinline__ int strip_log2(int cnt, int unit, int maxLog) {
+  int l = 0;
+  while (l < maxLog && cnt >= (unit << l)) ++l;      // cnt >= unit -> 2 strips, >= 2 unit -> 4, >= 4 unit -> 8
+  return l;
+}
+
 __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ tileCount, int* __restrict__ tileOffset,
-                                                        int* __restrict__ tileOrder, int nT,
+                                                        int* __restrict__ tileOrder, int nT, int nItems, int splitUnit, int maxLog,
                                                         const float* __restrict__ extr, const float* __restrict__ intr,
                                                         CamRec* __restrict__ cams) {
   __shared__ int warpSum[32];
   __shared__ int carry;
   __shared__ int bucketStart[33], bucketFill[33];
+  __shared__ int extraItems;
   const int view = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry = 0;
@@ -186,24 +197,45 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
     if (threadIdx.x == 0) carry += warpSum[31];
     __syncthreads();
   }
-  // counting sort of the tiles by floor(log2(count)) (33 buckets, 32 = heaviest ... 0 = empty)
+  // strips per tile: double the split unit until the extra items fit into the nItems - nT spare slots
+  int unit = splitUnit;
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    if (threadIdx.x == 0) extraItems = 0;
+    __syncthreads();
+    int extra = 0;
+    for (int i = threadIdx.x; i < nT; i += blockDim.x)
+      extra += (1 << strip_log2(tileCount[(size_t)view * nT + i], unit, maxLog)) - 1;
+    if (extra) atomicAdd(&extraItems, extra);
+    __syncthreads();
+    const int total = extraItems;
+    __syncthreads();
+    if (total <= nItems - nT) break;
+    unit = attempt < 6 ? unit * 2 : 0x7fffffff;      // last resort: no split at all
+  }
+  // counting sort of the items by floor(log2(bin size / K)) (33 buckets, 32 = heaviest ... 0 = empty)
   if (threadIdx.x < 33) { bucketStart[threadIdx.x] = 0; bucketFill[threadIdx.x] = 0; }
   __syncthreads();
   for (int i = threadIdx.x; i < nT; i += blockDim.x) {
     const int c = tileCount[(size_t)view * nT + i];
-    atomicAdd(&bucketStart[c > 0 ? 32 - __clz(c) : 0], 1);
+    const int l = strip_log2(c, unit, maxLog), w = c >> l;
+    atomicAdd(&bucketStart[w > 0 ? 32 - __clz(w) : 0], 1 << l);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     int run = 0;
     for (int k = 32; k >= 0; --k) { const int c = bucketStart[k]; bucketStart[k] = run; run += c; }
+    extraItems = run;                                  // = number of items of this view
   }
   __syncthreads();
+  int* order = tileOrder + (size_t)view * nItems;
   for (int i = threadIdx.x; i < nT; i += blockDim.x) {
     const int c = tileCount[(size_t)view * nT + i];
-    const int k = c > 0 ? 32 - __clz(c) : 0;
-    tileOrder[(size_t)view * nT + bucketStart[k] + atomicAdd(&bucketFill[k], 1)] = i;
+    const int l = strip_log2(c, unit, maxLog), w = c >> l;
+    const int k = w > 0 ? 32 - __clz(w) : 0;
+    const int pos = bucketStart[k] + atomicAdd(&bucketFill[k], 1 << l);
+    for (int sidx = 0; sidx < (1 << l); ++sidx) order[pos + sidx] = i | (sidx << 20) | (l << 24);
   }
+  for (int i = extraItems + threadIdx.x; i < nItems; i += blockDim.x) order[i] = -1;
   // one block per view: its spare time also produces the view's camera record (E^-1, (KE)^-1, ray
   // origin) for the raster kernel -- the reference spends a <<<1,1>>> launch on this
   if (threadIdx.x == 0) fill_camrec(extr, intr, cams, view);
@@ -354,10 +386,11 @@ __device__ __forceinline__ void edge_setup(float4 p0, float4 p1, float4 p2, floa
 struct RasterParams {
   const int4* faces4; const float4* proj; const float4* vscaled; const float4* vnorm4; const float4* vcol4;
   const CamRec* cams;
-  int* tileCount; int* tileCursor; const int* tileOffset; const int* tileOrder; const int* bigCount; const int* bigList; const int* bins;
+  int* tileCount; int* tileCursor; int* tileDone; const int* tileOffset; const int* tileOrder; const int* bigCount; const int* bigList; const int* bins;
   const float* texture; const float* texcoords; const float* sh_coeff;
   float* bary; int32_t* face; float* render;
-  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, V, batchDiv, interleave, hiz;
+  unsigned long long* ctaTrace;
+  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, spanZ;
   float cullMargin;
 };
 
@@ -414,9 +447,11 @@ __device__ __forceinline__ int key_lower_bound(float z0, float z1, float z2) {
 }
 
 // Shared-memory plan of raster_kernel (dynamic, carved by hand):
-//   zt[TS*TS] ZEntry | rayx,rayy,rayz[TS*TS] f32 (RC only) | per warp: rec[kBatch], erec[kBatch], startArr[60], spanStart[68], spanInfo[32]
+//   zt[TS*TS] ZEntry | rayx,rayy,rayz[TS*TS] f32 (RC only) | per warp: rec[kBatch], erec[kBatch], startArr[60], qStart[96], qInfo[64]
 constexpr int kBatch = 24;   // triangles a warp sets up at a time
-constexpr int kWarpSmemBytes = kBatch * (int)sizeof(TriRec) + kBatch * (int)sizeof(EdgeRec) + (60 + 68 + 32) * 4;
+constexpr int kQStart = 96;  // span queue: <= 31 spans left over + 32 new ones, + 33 sentinels for the 32-wide search
+constexpr int kQInfo = 64;
+constexpr int kWarpSmemBytes = kBatch * (int)sizeof(TriRec) + kBatch * (int)sizeof(EdgeRec) + (60 + kQStart + kQInfo) * 4;
 // RC = per-pixel ray cache in shared memory (3 CTAs/SM) or rays recomputed per use (4 CTAs/SM, <= 64 registers)
 // NTH = threads per tile CTA (256 or 128)
 template <int TS, bool RC, int NTH>
@@ -438,9 +473,14 @@ raster_kernel(const RasterParams p) {
   __shared__ int sMinK, sMaxK, sLate;
   __shared__ unsigned sZmax;
 
-  // 1-D grid, view fastest: the heaviest tiles of every view are scheduled first
+  // 1-D grid, view fastest: the heaviest work items of every view are scheduled first.
+  // item = tile | strip << 20 | log2(K) << 24: this CTA owns rows [rowLo, rowLo + rowN) of the tile
   const int view = blockIdx.x % p.V;
-  const int tile = p.tileOrder[(size_t)view * p.nT + blockIdx.x / p.V];
+  const int item = p.tileOrder[(size_t)view * p.nItems + blockIdx.x / p.V];
+  if (item < 0) return;                                // spare slot of the work list
+  const int tile = item & 0xfffff;
+  const int stripLog = item >> 24, rowN = TS >> stripLog, rowLo = ((item >> 20) & 15) * rowN;
+  const int qLo = rowLo * TS, qHi = (rowLo + rowN) * TS;
   const int b = view / p.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tileX0 = (tile % p.tilesX) * TS, tileY0 = (tile / p.tilesX) * TS;
@@ -448,9 +488,37 @@ raster_kernel(const RasterParams p) {
   const int cntSmall = p.tileCount[tidx];
   const int cntBig = p.bigCount[view];
   const size_t pixBase = (size_t)view * p.W * p.H;
+  if (p.ctaTrace && tid == 0) {
+    unsigned long long t; unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.ctaTrace[4 * (size_t)blockIdx.x] = t; p.ctaTrace[4 * (size_t)blockIdx.x + 1] = t;
+    p.ctaTrace[4 * (size_t)blockIdx.x + 2] = (unsigned long long)(cntSmall + cntBig); p.ctaTrace[4 * (size_t)blockIdx.x + 3] = smid;
+  }
 
   if (cntSmall == 0 && cntBig == 0) {
-    // empty tile: background only (face -1, bary 0, render (0,1,0): initializeDevice :80-89)
+    // empty tile: background only (face -1, bary 0, render (0,1,0): initializeDevice :80-89).
+    // Full-width tiles of 16-byte aligned images are written with 128-bit stores (6 per thread instead of 20).
+    const bool vec = ((p.W & 3) == 0) && tileX0 + TS <= p.W &&
+                     ((reinterpret_cast<uintptr_t>(p.face) | reinterpret_cast<uintptr_t>(p.bary) | reinterpret_cast<uintptr_t>(p.render)) & 15) == 0;
+    if (vec) {
+      const int rowsValid = min(TS, p.H - tileY0);
+      const size_t rowBase = pixBase + (size_t)tileY0 * p.W + tileX0;
+      for (int i = tid; i < rowsValid * (TS / 4); i += NTH) {
+        const int r = i / (TS / 4), c = i % (TS / 4);
+        reinterpret_cast<int4*>(p.face + rowBase + (size_t)r * p.W)[c] = make_int4(-1, -1, -1, -1);
+      }
+      for (int i = tid; i < rowsValid * (TS / 2); i += NTH) {
+        const int r = i / (TS / 2), c = i % (TS / 2);
+        reinterpret_cast<float4*>(p.bary + 2 * (rowBase + (size_t)r * p.W))[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int i = tid; i < rowsValid * (3 * TS / 4); i += NTH) {
+        const int r = i / (3 * TS / 4), c = i % (3 * TS / 4), m = c % 3;   // (0,1,0,0) (1,0,0,1) (0,0,1,0)
+        reinterpret_cast<float4*>(p.render + 3 * (rowBase + (size_t)r * p.W))[c] =
+            make_float4(m == 1 ? 1.f : 0.f, m == 0 ? 1.f : 0.f, m == 2 ? 1.f : 0.f, m == 1 ? 1.f : 0.f);
+      }
+      return;
+    }
     for (int q = tid; q < NPIX; q += NTH) {
       const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
       if (x < p.W && y < p.H) {
@@ -470,7 +538,7 @@ raster_kernel(const RasterParams p) {
   const F3 ros = mk3(cam.ros[0], cam.ros[1], cam.ros[2]);
 
   // z-tile clear + per-pixel ray cache (the ray depends on pixel and camera only)
-  for (int q = tid; q < NPIX; q += NTH) {
+  for (int q = qLo + tid; q < qHi; q += NTH) {
     { ZEntry e; e.key = kEmptyKey; e.a = 0.f; e.b = 0.f; zt[q] = e; }
     const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
     if (RC) {
@@ -492,7 +560,7 @@ raster_kernel(const RasterParams p) {
   EdgeRec* erec = reinterpret_cast<EdgeRec*>(wbase + kBatch * sizeof(TriRec));
   int* startArr = reinterpret_cast<int*>(wbase + kBatch * (sizeof(TriRec) + sizeof(EdgeRec)));
   int* mySpanStart = startArr + 60;
-  int* mySpanInfo = mySpanStart + 68;
+  int* mySpanInfo = mySpanStart + kQStart;
 
   // exact test + atomicMin into the z-tile for one (triangle k of the batch, tile pixel q) pair
   auto exact_pair = [&](int k, int q) {
@@ -502,13 +570,14 @@ raster_kernel(const RasterParams p) {
     TriSetup ts;
     ts.v0 = mk3(r0.x, r0.y, r0.z); ts.v1 = mk3(r0.w, r1.x, r1.y); ts.v2 = mk3(r1.z, r1.w, r2.x);
     ts.N = mk3(r2.y, r2.z, r2.w); ts.num = r3.x; ts.den = r3.y;
-    const F3 rd = ray_of(q);
     float a, bq, c;
     // conservative early-z: r4.z is a lower bound of every depth key this triangle can produce
     // (0.99 * min vertex depth, only for triangles with zmax <= 2 zmin); if even that is behind the
     // pixel's current winner the pair cannot win (ties have equal keys and are never skipped)
     ZEntry cur = zt[q];
     const bool behind = (unsigned)(r4.z ^ 0x80000000) > (unsigned)(cur.key >> 32);
+    if (p.spanZ && behind) return;
+    const F3 rd = ray_of(q);
     if (hit_exact(ts, ros, rd, a, bq, c, behind)) {
       const int depth = depth_key_exact(a, bq, c, r3.z, r3.w, __int_as_float(r4.x));
       ZEntry nv;
@@ -553,7 +622,7 @@ raster_kernel(const RasterParams p) {
     __syncthreads();                                  // pass 0 complete
     if (sLate == 0) break;                            // nothing was deferred
     unsigned m = 0u;
-    for (int q = tid; q < NPIX; q += NTH) {
+    for (int q = qLo + tid; q < qHi; q += NTH) {
       const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
       if (x < p.W && y < p.H) m = max(m, (unsigned)(zt[q].key >> 32));
     }
@@ -582,7 +651,7 @@ raster_kernel(const RasterParams p) {
       const float4 p0 = __ldg(pj + fc.x), p1 = __ldg(pj + fc.y), p2 = __ldg(pj + fc.z);
       const int4 bb = bbox_exact(p0, p1, p2, p.W, p.H);
       const int cx0 = max(bb.x, tileX0), cx1 = min(bb.z, tileX0 + TS - 1);
-      const int cy0 = max(bb.y, tileY0), cy1 = min(bb.w, tileY0 + TS - 1);
+      const int cy0 = max(bb.y, tileY0 + rowLo), cy1 = min(bb.w, tileY0 + rowLo + rowN - 1);
       const int w = cx1 - cx0 + 1, h = cy1 - cy0 + 1;
       const int klb = key_lower_bound(p0.z, p1.z, p2.z);
       const bool late = klb > thr;                     // belongs to pass 1
@@ -622,6 +691,7 @@ raster_kernel(const RasterParams p) {
     if (lane == 0) startArr[ntri + 32] = 0x7fffffff;
     __syncwarp();
     int K0 = 0;
+    int qn = 0, qtot = 0;                                // span queue: spans / pixels waiting for the exact test
     for (int fb = 0; fb < nrows; fb += 32) {
       // (1) one bbox row per lane: which triangle, which row
       const int s = startArr[K0 + 1 + lane];
@@ -646,40 +716,80 @@ raster_kernel(const RasterParams p) {
         { const float t = s1 * e2.z; if (e0.w > 0.f) xlo = fmaxf(xlo, t); else if (e0.w < 0.f) xhi = fminf(xhi, t); else ok = ok && (s1 >= 0.f); }
         { const float t = s2 * e2.w; if (e1.z > 0.f) xlo = fmaxf(xlo, t); else if (e1.z < 0.f) xhi = fminf(xhi, t); else ok = ok && (s2 >= 0.f); }
         // 1e-3 px of slack for the rounding of t_i (|t| <= ~64 wherever it matters), then clamp to the bbox row
-        const int xl = max(x0, (int)ceilf(fmaxf(xlo - 1.0e-3f, -1.0f)));
-        const int xr = min(x0 + w - 1, (int)floorf(fminf(xhi + 1.0e-3f, 64.0f)));
+        int xl = max(x0, (int)ceilf(fmaxf(xlo - 1.0e-3f, -1.0f)));
+        int xr = min(x0 + w - 1, (int)floorf(fminf(xhi + 1.0e-3f, 64.0f)));
+        if (p.spanZ && (p.spanZ == 1 || pass == 1) && ok && xr >= xl) {
+          // span-level early z: trim the span to the pixels whose current winner is NOT provably in
+          // front of everything this triangle can produce (depth-key lower bound, see key_lower_bound).
+          // Keys only decrease, so a stale read keeps a pixel that could have been dropped, never the
+          // other way round; dropped pairs cannot win the depth test => bit-identical result.
+          const unsigned kb = (unsigned)(rec[k].pad0 ^ 0x80000000);
+          const unsigned* zhi = reinterpret_cast<const unsigned*>(zt + ly * TS) + 1;
+          int first = 0x7fffffff, last = -1;
+          for (int x = xl; x <= xr; ++x)
+            if (!(kb > zhi[4 * x])) { first = min(first, x); last = x; }
+          xl = first; xr = last;
+        }
         cnt = ok ? max(0, xr - xl + 1) : 0;
         info = (k << 10) | (ly << 5) | xl;
       }
-      // (3) compact the non-empty spans of these 32 rows, (4) expand them 32 pixels at a time
+      // (3) append the non-empty spans of these 32 rows to the warp's span queue.  The queue is
+      // drained in FULL groups of 32 pixels; what is left (< 32 pixels) waits for the spans of the
+      // next 32 rows, so the exact test runs with all lanes busy even when the depth culling above has
+      // thinned the spans out.  The queue is flushed completely at the end of the batch (rec[] is reused).
       int incl = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += y; }
       const int total = __shfl_sync(FULL_MASK, incl, 31);
       const unsigned nz = __ballot_sync(FULL_MASK, cnt > 0);
-      const int nspan = __popc(nz);
       if (cnt > 0) {
-        const int r = __popc(nz & ((1u << lane) - 1u));
-        mySpanStart[r] = incl - cnt;
+        const int r = qn + __popc(nz & ((1u << lane) - 1u));
+        mySpanStart[r] = qtot + incl - cnt;
         mySpanInfo[r] = info;
       }
-      mySpanStart[nspan + lane] = 0x7fffffff;
-      if (lane == 0) mySpanStart[nspan + 32] = 0x7fffffff;
+      qn += __popc(nz);
+      qtot += total;
+      mySpanStart[qn + lane] = 0x7fffffff;
+      if (lane == 0) mySpanStart[qn + 32] = 0x7fffffff;
       __syncwarp();
+      const bool lastRows = fb + 32 >= nrows;
+      const int limit = lastRows ? qtot : (qtot & ~31);
+      // (4) expand the queued spans 32 pixels at a time
       int S0 = 0;
-      for (int t0 = 0; t0 < total; t0 += 32) {
+      for (int t0 = 0; t0 < limit; t0 += 32) {
         const int ss = mySpanStart[S0 + 1 + lane];
         const unsigned sb = (ss < t0 + 32) ? (1u << (ss - t0)) : 0u;
         const unsigned sm = __reduce_or_sync(FULL_MASK, sb);
         const int si = S0 + __popc(sm & ((2u << lane) - 1u));
         S0 += __popc(sm);
         const int t = t0 + lane;
-        if (t < total) {
+        if (t < limit) {
           const int inf = mySpanInfo[si];
           exact_pair(inf >> 10, ((inf >> 5) & 31) * TS + (inf & 31) + (t - mySpanStart[si]));
         }
       }
       __syncwarp();
+      // (5) keep the unconsumed tail: span S0 holds pixel `limit` (partly consumed), the later ones are untouched
+      if (limit == qtot) { qn = 0; qtot = 0; }
+      else if (limit > 0) {
+        if (mySpanStart[S0 + 1] == limit) ++S0;           // span S0 ended exactly at `limit`: nothing of it is left
+        const int e0 = S0 + lane, e1 = S0 + lane + 32;
+        int st0 = 0, in0 = 0, st1 = 0, in1 = 0;
+        if (e0 < qn) { st0 = mySpanStart[e0]; in0 = mySpanInfo[e0]; }
+        if (e1 < qn) { st1 = mySpanStart[e1]; in1 = mySpanInfo[e1]; }
+        __syncwarp();
+        if (e0 < qn) {
+          const int used = max(limit - st0, 0);          // > 0 only for the first kept span
+          mySpanStart[lane] = max(st0 - limit, 0);
+          mySpanInfo[lane] = in0 + used;                  // xl advances by the consumed pixels (stays < 32)
+        }
+        if (e1 < qn) { mySpanStart[lane + 32] = st1 - limit; mySpanInfo[lane + 32] = in1; }
+        qn -= S0; qtot -= limit;
+        __syncwarp();
+        mySpanStart[qn + lane] = 0x7fffffff;
+        if (lane == 0) mySpanStart[qn + 32] = 0x7fffffff;
+        __syncwarp();
+      }
     }
   }
   }   // pass
@@ -689,7 +799,7 @@ raster_kernel(const RasterParams p) {
   const float4* vn = p.vnorm4 + (size_t)b * p.N;
   const float4* vc = p.vcol4 + (size_t)b * p.N;
   const bool doShade = (p.shading == GVV_SHADING_SHADED && p.albedo != GVV_ALBEDO_NORMAL) || p.albedo == GVV_ALBEDO_LIGHTING;
-  for (int q = tid; q < NPIX; q += NTH) {
+  for (int q = qLo + tid; q < qHi; q += NTH) {
     const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
     if (x >= p.W || y >= p.H) continue;
     const size_t pix = pixBase + (size_t)y * p.W + x;
@@ -741,7 +851,15 @@ raster_kernel(const RasterParams p) {
     reinterpret_cast<float2*>(p.bary)[pix] = make_float2(a, bq);
     p.render[3 * pix + 0] = cr; p.render[3 * pix + 1] = cg; p.render[3 * pix + 2] = cb;
   }
-  if (tid == 0) { p.tileCount[tidx] = 0; p.tileCursor[tidx] = 0; }   // self-cleaning scratch
+  // self-cleaning scratch: the last strip of the tile to finish resets the tile's counters (every strip
+  // read them before it got here)
+  if (tid == 0) {
+    if (stripLog == 0 || atomicAdd(p.tileDone + tidx, 1) == (1 << stripLog) - 1) { p.tileCount[tidx] = 0; p.tileCursor[tidx] = 0; p.tileDone[tidx] = 0; }
+  }
+  if (p.ctaTrace) {
+    __syncthreads();
+    if (tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.ctaTrace[4 * (size_t)blockIdx.x + 1] = t; }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -811,7 +929,10 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   tm->end(st);
   ++launches;
   tm->begin(K_BIN_SCAN, st);
-  bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.nT, a.extrinsics, a.intrinsics, a.s.cams);
+  const int nItems = a.nT + a.nT / 2;                  // Scratch::tileOrder is sized for this (gvv_api.cu)
+  const int maxLog = a.splitUnit > 0 ? (a.tile == 32 ? 3 : 2) : 0;
+  bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.nT, nItems, a.splitUnit > 0 ? a.splitUnit : 1, maxLog,
+                                      a.extrinsics, a.intrinsics, a.s.cams);
   tm->end(st);
   ++launches;
   tm->begin(K_BIN_FILL, st);
@@ -826,13 +947,13 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   ++launches;
   RasterParams p;
   p.faces4 = a.faces4; p.proj = a.s.proj; p.vscaled = a.s.vscaled; p.vnorm4 = a.s.vnorm4; p.vcol4 = a.s.vcol4;
-  p.cams = a.s.cams; p.tileCount = a.s.tileCount; p.tileCursor = a.s.tileCursor; p.tileOffset = a.s.tileOffset; p.tileOrder = a.s.tileOrder; p.V = V;
+  p.cams = a.s.cams; p.tileCount = a.s.tileCount; p.tileCursor = a.s.tileCursor; p.tileDone = a.s.tileDone; p.nItems = nItems; p.tileOffset = a.s.tileOffset; p.tileOrder = a.s.tileOrder; p.V = V;
   p.bigCount = a.s.bigCount; p.bigList = a.s.bigList; p.bins = a.s.bins;
   p.texture = a.texture; p.texcoords = a.texcoords; p.sh_coeff = a.sh_coeff;
-  p.bary = a.bary; p.face = a.face; p.render = a.render;
+  p.bary = a.bary; p.face = a.face; p.render = a.render; p.ctaTrace = a.s.ctaTrace;
   p.C = a.C; p.N = a.N; p.F = a.F; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
-  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv; p.interleave = a.interleave; p.hiz = a.hiz;
-  const dim3 gridT((unsigned)a.nT * (unsigned)V);
+  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv; p.interleave = a.interleave; p.hiz = a.hiz; p.spanZ = a.spanZ;
+  const dim3 gridT((unsigned)nItems * (unsigned)V);
   tm->begin(K_RASTER, st);
   static bool attrSet = false;
   if (!attrSet) {   // > 48 KB of dynamic shared memory needs the opt-in (once per process and device function)

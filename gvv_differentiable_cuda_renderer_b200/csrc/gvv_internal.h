@@ -24,7 +24,8 @@ struct Scratch {
   int* tileCount = nullptr;      // [V*nT] self-cleaning (the raster kernel zeroes its own entry)
   int* tileCursor = nullptr;     // [V*nT] self-cleaning
   int* tileOffset = nullptr;     // [V*nT]
-  int* tileOrder = nullptr;      // [V*nT] tiles of a view sorted by bin size, heaviest first
+  int* tileOrder = nullptr;      // [V*(nT+nT/2)] raster work items (tile strips) of a view, heaviest first; -1 = unused slot
+  int* tileDone = nullptr;       // [V*nT] strips of a split tile that have finished; self-cleaning
   int* bigCount = nullptr;       // [V]    zeroed by camera_kernel of the next call
   int* bigList = nullptr;        // [V*F]
   int* bins = nullptr;           // [V*F*kMaxSmallTiles]
@@ -32,6 +33,7 @@ struct Scratch {
   float4* bpos4 = nullptr;       // [B*N]  backward: repacked vertex_pos (raw)
   float4* bcol4 = nullptr;       // [B*N]  backward: repacked vertex_color
   float4* bnor4 = nullptr;       // [V*N]  backward: repacked vertex_normal input
+  unsigned long long* ctaTrace = nullptr;   // [V*nT*4] debug (option cta_trace): globaltimer start, end, bin size, SM id per raster CTA
 };
 
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py roofline leg).
@@ -58,6 +60,9 @@ struct gvv_renderer {
   int F = 0, N = 0, C = 0, W = 0, H = 0;
   int albedo = 0, shading = 0, imgFilter = 1, texFilter = 1, computeNormalMap = 0;
   int tile = 32, tilesX = 0, tilesY = 0, nT = 0;
+  int splitUnit = 384;        // raster: a bin of >= splitUnit (2x, 4x) triangles is cut into 2 (4, 8) strips with a CTA each; 0 = never
+  int ctaTrace = 0;           // debug: record per-CTA start/end times of the raster kernel
+  int spanZ = 1;              // raster: trim every row span to the pixels whose current winner the triangle could still beat
   int hiz = 1;                // raster: two-pass hierarchical z (skips triangles behind the whole tile)
   int interleave = 1;         // raster: batch j takes bin entries j, j+nBatches, ... instead of a contiguous chunk
   int ctaThreads = 256;       // raster: threads per tile CTA (256 | 128)
@@ -80,7 +85,7 @@ namespace gvv {
 
 struct FwdArgs {
   int B, C, N, F, W, H, texH, texW, albedo, shading;
-  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz;
+  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, spanZ, splitUnit;
   float cullMargin;
   const float *vertex_pos, *vertex_color, *texture, *sh_coeff, *extrinsics, *intrinsics;
   const float* texcoords;
