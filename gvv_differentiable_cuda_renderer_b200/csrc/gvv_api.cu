@@ -123,6 +123,13 @@ extern "C" int gvv_create(const gvv_desc* d, gvv_handle* out) {
   h->texFilter = d->texture_filter_size;
   h->computeNormalMap = d->compute_normal_map ? 1 : 0;
   set_tile(h, 32);
+  // side stream + fork/join events of the heavy-tile raster launch (gvv_forward.cu); failure just disables that path
+  if (cudaStreamCreateWithFlags(&h->sideStream, cudaStreamNonBlocking) != cudaSuccess) h->sideStream = nullptr;
+  if (cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming) != cudaSuccess) {
+    if (h->sideStream) cudaStreamDestroy(h->sideStream);
+    h->sideStream = nullptr;
+  }
+  cudaGetLastError();
 
   // topology: faces padded to int4; vertex -> incident faces CSR by counting sort, O(N+F)
   // (reference: O(N*F) double loop, CUDABasedRasterization.cpp:125-154; same ascending face order;
@@ -171,6 +178,9 @@ extern "C" int gvv_destroy(gvv_handle h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   free_scratch(h->s);
+  if (h->sideStream) cudaStreamDestroy(h->sideStream);
+  if (h->evFork) cudaEventDestroy(h->evFork);
+  if (h->evJoin) cudaEventDestroy(h->evJoin);
   if (h->timer.ev) { for (int i = 0; i < 2 * KernelTimer::kCap; ++i) cudaEventDestroy(h->timer.ev[i]); delete[] h->timer.ev; delete[] h->timer.slot; }
   cudaFree(h->faces4); cudaFree(h->texcoords); cudaFree(h->vfOffsets); cudaFree(h->vfList); cudaFree(h->texelTable);
   delete h;
@@ -197,6 +207,8 @@ extern "C" int gvv_set_option(gvv_handle h, const char* key, int32_t value) {
   if (!strcmp(key, "cta_threads")) { if (value != 128 && value != 256) return fail(GVV_EINVAL, "cta_threads must be 128 or 256"); h->ctaThreads = value; return GVV_OK; }
   if (!strcmp(key, "span_z")) { if (value < 0 || value > 2) return fail(GVV_EINVAL, "span_z must be 0 (off), 1 (both passes) or 2 (far pass only)"); h->spanZ = value; return GVV_OK; }
   if (!strcmp(key, "cta_trace")) { cudaSetDevice(h->device); cudaDeviceSynchronize(); free_scratch(h->s); h->ctaTrace = value ? 1 : 0; return GVV_OK; }   // scratch is re-allocated by the next call
+  if (!strcmp(key, "spread_empty")) { h->spreadEmpty = value ? 1 : 0; return GVV_OK; }
+  if (!strcmp(key, "heavy_thr")) { if (value < 0) return fail(GVV_EINVAL, "heavy_thr must be >= 0"); h->heavyThr = value; return GVV_OK; }
   if (!strcmp(key, "split_unit")) { if (value < 0) return fail(GVV_EINVAL, "split_unit must be >= 0"); h->splitUnit = value; return GVV_OK; }
   if (!strcmp(key, "hiz")) { h->hiz = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "interleave")) { h->interleave = value ? 1 : 0; return GVV_OK; }
@@ -241,7 +253,7 @@ extern "C" int gvv_forward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
   FwdArgs a;
   a.B = B; a.C = h->C; a.N = h->N; a.F = h->F; a.W = h->W; a.H = h->H; a.texH = texH; a.texW = texW;
   a.albedo = h->albedo; a.shading = h->shading;
-  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin; a.rayCache = h->rayCache; a.batchDiv = h->batchDiv; a.ctaThreads = h->ctaThreads; a.interleave = h->interleave; a.hiz = h->hiz; a.spanZ = h->spanZ; a.splitUnit = h->splitUnit;
+  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin; a.rayCache = h->rayCache; a.batchDiv = h->batchDiv; a.ctaThreads = h->ctaThreads; a.interleave = h->interleave; a.hiz = h->hiz; a.spanZ = h->spanZ; a.splitUnit = h->splitUnit; a.heavyThr = h->heavyThr; a.spreadEmpty = h->spreadEmpty; a.sideStream = h->sideStream; a.evFork = h->evFork; a.evJoin = h->evJoin;
   a.vertex_pos = vertex_pos; a.vertex_color = vertex_color; a.texture = texture; a.sh_coeff = sh_coeff;
   a.extrinsics = extrinsics; a.intrinsics = intrinsics; a.texcoords = h->texcoords;
   a.faces4 = h->faces4; a.vfOffsets = h->vfOffsets; a.vfList = h->vfList;

@@ -166,6 +166,7 @@ __device__ __forceinline__ int strip_log2(int cnt, int unit, int maxLog) {
 
 __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ tileCount, int* __restrict__ tileOffset,
                                                         int* __restrict__ tileOrder, int nT, int nItems, int splitUnit, int maxLog,
+                                                        int heavyThr, int heavySlots, int spreadEmpty,
                                                         const float* __restrict__ extr, const float* __restrict__ intr,
                                                         CamRec* __restrict__ cams) {
   __shared__ int warpSum[32];
@@ -232,8 +233,21 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
     const int c = tileCount[(size_t)view * nT + i];
     const int l = strip_log2(c, unit, maxLog), w = c >> l;
     const int k = w > 0 ? 32 - __clz(w) : 0;
-    const int pos = bucketStart[k] + atomicAdd(&bucketFill[k], 1 << l);
-    for (int sidx = 0; sidx < (1 << l); ++sidx) order[pos + sidx] = i | (sidx << 20) | (l << 24);
+    const int pos0 = bucketStart[k] + atomicAdd(&bucketFill[k], 1 << l);
+    // Empty tiles (bucket 0; pure 24 B/px background stores, HBM-bound) are spread evenly between the non-empty
+    // ones (ALU-bound) instead of forming the tail of the launch: non-empty i moves to i + floor(i n0/n1),
+    // empty j fills the gaps -- a bijection on [0, n0 + n1) that keeps the heaviest-first order of the non-empty items.
+    const int n1 = bucketStart[0], n0 = extraItems - n1;     // non-empty / empty items of this view
+    for (int sidx = 0; sidx < (1 << l); ++sidx) {
+      int pos = pos0 + sidx;
+      if (spreadEmpty && n0 > 0 && n1 > 0) {
+        if (k > 0) pos += (int)(((long long)pos * n0) / n1);
+        else { const int j = pos - n1; pos = j + min(n1, (int)((((long long)(j + 1)) * n1 + n0 - 1) / n0)); }
+      }
+      // bit 28: the item is rasterised by the 1024-thread launch (one whole SM per tile) instead of a 256-thread CTA
+      const int heavy = (heavyThr > 0 && w >= heavyThr && pos < heavySlots) ? (1 << 28) : 0;
+      order[pos] = i | (sidx << 20) | (l << 24) | heavy;
+    }
   }
   for (int i = extraItems + threadIdx.x; i < nItems; i += blockDim.x) order[i] = -1;
   // one block per view: its spare time also produces the view's camera record (E^-1, (KE)^-1, ray
@@ -390,7 +404,7 @@ struct RasterParams {
   const float* texture; const float* texcoords; const float* sh_coeff;
   float* bary; int32_t* face; float* render;
   unsigned long long* ctaTrace;
-  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, spanZ;
+  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, spanZ, role;
   float cullMargin;
 };
 
@@ -478,8 +492,9 @@ raster_kernel(const RasterParams p) {
   const int view = blockIdx.x % p.V;
   const int item = p.tileOrder[(size_t)view * p.nItems + blockIdx.x / p.V];
   if (item < 0) return;                                // spare slot of the work list
+  if (((item >> 28) & 1) != p.role) return;            // heavy items belong to the 1024-thread launch (role 1), the rest to role 0
   const int tile = item & 0xfffff;
-  const int stripLog = item >> 24, rowN = TS >> stripLog, rowLo = ((item >> 20) & 15) * rowN;
+  const int stripLog = (item >> 24) & 15, rowN = TS >> stripLog, rowLo = ((item >> 20) & 15) * rowN;
   const int qLo = rowLo * TS, qHi = (rowLo + rowN) * TS;
   const int b = view / p.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -930,9 +945,14 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   ++launches;
   tm->begin(K_BIN_SCAN, st);
   const int nItems = a.nT + a.nT / 2;                  // Scratch::tileOrder is sized for this (gvv_api.cu)
+  // Heavy bins (>= heavyThr triangles among the kHeavySlots heaviest items of a view) get a 1024-thread CTA, i.e.
+  // a whole SM, from a second launch on a side stream: a 256-thread CTA shares its SM with three others and
+  // would make the tile the critical path of the launch (measured: 236 us of a 274 us launch).
+  constexpr int kHeavySlots = 32;
+  const bool useHeavy = a.heavyThr > 0 && a.tile == 32 && !a.rayCache && a.ctaThreads == 256 && a.sideStream != nullptr;
   const int maxLog = a.splitUnit > 0 ? (a.tile == 32 ? 3 : 2) : 0;
   bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.nT, nItems, a.splitUnit > 0 ? a.splitUnit : 1, maxLog,
-                                      a.extrinsics, a.intrinsics, a.s.cams);
+                                      useHeavy ? a.heavyThr : 0, kHeavySlots, a.spreadEmpty, a.extrinsics, a.intrinsics, a.s.cams);
   tm->end(st);
   ++launches;
   tm->begin(K_BIN_FILL, st);
@@ -959,11 +979,25 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   if (!attrSet) {   // > 48 KB of dynamic shared memory needs the opt-in (once per process and device function)
 #define GVV_RASTER_ATTR(TS, RC, NTH) cudaFuncSetAttribute(raster_kernel<TS, RC, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<TS, RC, NTH>())
     GVV_RASTER_ATTR(16, true, 256); GVV_RASTER_ATTR(32, true, 256); GVV_RASTER_ATTR(16, false, 256); GVV_RASTER_ATTR(32, false, 256);
-    GVV_RASTER_ATTR(16, false, 128); GVV_RASTER_ATTR(32, false, 128);
+    GVV_RASTER_ATTR(16, false, 128); GVV_RASTER_ATTR(32, false, 128); GVV_RASTER_ATTR(32, false, 1024);
 #undef GVV_RASTER_ATTR
     attrSet = true;
   }
-#define GVV_RASTER_LAUNCH(TS, RC, NTH) raster_kernel<TS, RC, NTH><<<gridT, NTH, raster_smem_bytes<TS, RC, NTH>(), st>>>(p)
+  // fork: the heavy launch goes FIRST and on the caller's stream, so that its one-SM CTAs are placed while the
+  // SMs are empty; the 256-thread launch follows on the side stream (a CTA that needs a whole SM would
+  // otherwise starve behind the small ones until the very end of the launch -- measured)
+  cudaStream_t ls = st;
+  if (useHeavy) {
+    RasterParams ph = p;
+    ph.role = 1;
+    cudaEventRecord(a.evFork, st);
+    raster_kernel<32, false, 1024><<<dim3((unsigned)kHeavySlots * (unsigned)V), 1024, raster_smem_bytes<32, false, 1024>(), st>>>(ph);
+    cudaStreamWaitEvent(a.sideStream, a.evFork, 0);
+    ls = a.sideStream;
+    ++launches;
+  }
+  p.role = 0;
+#define GVV_RASTER_LAUNCH(TS, RC, NTH) raster_kernel<TS, RC, NTH><<<gridT, NTH, raster_smem_bytes<TS, RC, NTH>(), ls>>>(p)
   if (a.tile == 16) {
     if (a.rayCache) GVV_RASTER_LAUNCH(16, true, 256);
     else if (a.ctaThreads == 128) GVV_RASTER_LAUNCH(16, false, 128);
@@ -974,6 +1008,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
     else GVV_RASTER_LAUNCH(32, false, 256);
   }
 #undef GVV_RASTER_LAUNCH
+  if (useHeavy) { cudaEventRecord(a.evJoin, a.sideStream); cudaStreamWaitEvent(st, a.evJoin, 0); }   // join
   tm->end(st);
   ++launches;
   return launch_ok() ? launches : -1;

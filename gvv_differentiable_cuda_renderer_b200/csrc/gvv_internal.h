@@ -60,9 +60,12 @@ struct gvv_renderer {
   int F = 0, N = 0, C = 0, W = 0, H = 0;
   int albedo = 0, shading = 0, imgFilter = 1, texFilter = 1, computeNormalMap = 0;
   int tile = 32, tilesX = 0, tilesY = 0, nT = 0;
-  int splitUnit = 384;        // raster: a bin of >= splitUnit (2x, 4x) triangles is cut into 2 (4, 8) strips with a CTA each; 0 = never
+  int spreadEmpty = 0;        // raster: interleave the (HBM-bound) empty tiles with the (ALU-bound) non-empty ones
+  int heavyThr = 0;         // raster: bins of >= heavyThr triangles are rasterised by 1024-thread CTAs on a side stream; 0 = off
+  cudaStream_t sideStream = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  int splitUnit = 0;          // raster: a bin of >= splitUnit (2x, 4x) triangles is cut into 2 (4, 8) strips with a CTA each; 0 = never (measured slower: every strip re-scans the bin)
   int ctaTrace = 0;           // debug: record per-CTA start/end times of the raster kernel
-  int spanZ = 1;              // raster: trim every row span to the pixels whose current winner the triangle could still beat
+  int spanZ = 2;              // raster: trim every row span to the pixels whose current winner the triangle could still beat (1 = both passes, 2 = far pass only)
   int hiz = 1;                // raster: two-pass hierarchical z (skips triangles behind the whole tile)
   int interleave = 1;         // raster: batch j takes bin entries j, j+nBatches, ... instead of a contiguous chunk
   int ctaThreads = 256;       // raster: threads per tile CTA (256 | 128)
@@ -85,7 +88,8 @@ namespace gvv {
 
 struct FwdArgs {
   int B, C, N, F, W, H, texH, texW, albedo, shading;
-  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, spanZ, splitUnit;
+  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, spanZ, splitUnit, heavyThr, spreadEmpty;
+  cudaStream_t sideStream; cudaEvent_t evFork, evJoin;
   float cullMargin;
   const float *vertex_pos, *vertex_color, *texture, *sh_coeff, *extrinsics, *intrinsics;
   const float* texcoords;
