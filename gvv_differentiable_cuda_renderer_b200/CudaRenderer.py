@@ -20,11 +20,11 @@ _IDENT_CACHE = {}
 _HANDLE_CACHE_MAX = 16
 
 
-def _get_handle(faces, texcoords, N, C, U, V, albedo, shading, ifs, tfs, normal_map, device):
+def _get_handle(faces, texcoords, N, C, U, V, albedo, shading, ifs, tfs, normal_map, device, tex_bilinear=False):
     """TF caches one OpKernel per attribute set; this is the same cache for gvv handles, so that
     building the layer every iteration of a fitting loop (as the reference's scripts do,
     python/test_gradients_VertexColor.py:104-121) does not rebuild topology or scratch."""
-    attrs = (int(N), int(C), int(U), int(V), albedo, shading, int(ifs), int(tfs), bool(normal_map), str(device))
+    attrs = (int(N), int(C), int(U), int(V), albedo, shading, int(ifs), int(tfs), bool(normal_map), str(device), bool(tex_bilinear))
     # fast path: the very same attribute objects as last time (a fitting loop passes the same lists)
     ident = (id(faces), id(texcoords)) + attrs
     hit = _IDENT_CACHE.get(ident)
@@ -36,6 +36,8 @@ def _get_handle(faces, texcoords, N, C, U, V, albedo, shading, ifs, tfs, normal_
     h = _HANDLE_CACHE.get(key)
     if h is None:
         h = _native.NativeRenderer(f, t, N, C, U, V, albedo, shading, ifs, tfs, normal_map, device)
+        if tex_bilinear:
+            h.set_option("texture_bilinear", 1)
         _HANDLE_CACHE[key] = h
         while len(_HANDLE_CACHE) > _HANDLE_CACHE_MAX:
             _HANDLE_CACHE.popitem(last=False)[1].close()
@@ -125,7 +127,8 @@ class CudaRendererGpu:
                  intrinsics_input=[],
 
                  nodeName='CudaRenderer',
-                 device=None):
+                 device=None,
+                 textureBilinear_attr=False):
         self.faces_attr = faces_attr
         self.texCoords_attr = texCoords_attr
         self.numberOfVertices_attr = numberOfVertices_attr
@@ -138,6 +141,9 @@ class CudaRendererGpu:
         self.texture_filter_size_attr = texture_filter_size_attr
         self.compute_normal_map_attr = compute_normal_map_attr
         self.nodeName = nodeName
+        # extension (not in the reference signature, default = reference behaviour): bilinear texture fetch and
+        # weighted 4-texel texture-gradient scatter, the variants the reference has commented out
+        self.textureBilinear_attr = bool(textureBilinear_attr)
 
         if device is None:
             device = vertexPos_input.device if isinstance(vertexPos_input, torch.Tensor) and vertexPos_input.is_cuda \
@@ -153,7 +159,8 @@ class CudaRendererGpu:
 
         self._handle = _get_handle(faces_attr, texCoords_attr, numberOfVertices_attr, numberOfCameras_attr,
                                    renderResolutionU_attr, renderResolutionV_attr, albedoMode_attr, shadingMode_attr,
-                                   image_filter_size_attr, texture_filter_size_attr, compute_normal_map_attr, self.device)
+                                   image_filter_size_attr, texture_filter_size_attr, compute_normal_map_attr, self.device,
+                                   self.textureBilinear_attr)
         self.cudaRendererOperator = _CudaRendererFn.apply(self._handle, self.vertexPos_input, self.vertexColor_input,
                                                           self.texture_input, self.shCoeff_input, self.targetImage_input,
                                                           self.extrinsics_input, self.intrinsics_input)

@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libgvv_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
-SOURCES = ["gvv_api.cu", "gvv_forward.cu", "gvv_backward.cu", "gvv_normalmap.cu", "gvv_microbench.cu"]
+SOURCES = ["gvv_api.cu", "gvv_forward.cu", "gvv_backward.cu", "gvv_normalmap.cu", "gvv_helpers.cu", "gvv_microbench.cu"]
 
 ALBEDO_MODES = {"vertexColor": 0, "textured": 1, "normal": 2, "lighting": 3, "foregroundMask": 4}
 SHADING_MODES = {"shaded": 0, "shadeless": 1}
@@ -53,7 +53,8 @@ _lib = None
 # every symbol include/gvv_b200.h declares
 EXPORTS = ["gvv_create", "gvv_destroy", "gvv_forward", "gvv_backward", "gvv_last_error", "gvv_launch_count",
            "gvv_debug_copy", "gvv_debug_eval", "gvv_set_option", "gvv_bench_atomics",
-           "gvv_kernel_count", "gvv_kernel_name", "gvv_kernel_times"]
+           "gvv_kernel_count", "gvv_kernel_name", "gvv_kernel_times",
+           "gvv_gaussian_smooth", "gvv_image_gradient", "gvv_set_target_gradient"]
 
 
 def lib():
@@ -88,6 +89,12 @@ def lib():
         L.gvv_kernel_times.restype = ctypes.c_int
         L.gvv_bench_atomics.argtypes = [i32, i32, i64, i64, i32, ctypes.POINTER(ctypes.c_double)]
         L.gvv_bench_atomics.restype = ctypes.c_int
+        L.gvv_gaussian_smooth.argtypes = [i32, i64, i32, i32, i32, vp, vp, vp, vp, vp]
+        L.gvv_gaussian_smooth.restype = ctypes.c_int
+        L.gvv_image_gradient.argtypes = [i32, i64, i32, i32, i32, vp, vp, vp, vp]
+        L.gvv_image_gradient.restype = ctypes.c_int
+        L.gvv_set_target_gradient.argtypes = [vp, vp, vp]
+        L.gvv_set_target_gradient.restype = ctypes.c_int
         _lib = L
     return _lib
 
@@ -226,6 +233,13 @@ class NativeRenderer:
                                       _ptr(gsh), self._stream()), "gvv_backward")
         return gpos, gcol, gtex, gsh
 
+    def set_target_gradient(self, d_du, d_dv):
+        """Hand the precomputed target-image gradient (image_gradient(target, image_filter_size)) to the
+        backward's model-to-data term; (None, None) restores the per-pixel recomputation.  The tensors
+        must stay alive (and unchanged) while they are set."""
+        self._target_grad_cache = (d_du, d_dv)
+        _check(lib().gvv_set_target_gradient(self._h, _ptr(d_du), _ptr(d_dv)), "gvv_set_target_gradient")
+
     def debug_copy(self, which, nbytes):
         buf = np.empty(nbytes, dtype=np.uint8)
         n = lib().gvv_debug_copy(self._h, which, buf.ctypes.data, nbytes, self._stream())
@@ -262,3 +276,31 @@ def bench_atomics(kind, n_addr, n_ops, iters=10, device=0):
     out = ctypes.c_double(0.0)
     _check(lib().gvv_bench_atomics(device, kind, n_addr, n_ops, iters, ctypes.byref(out)), "gvv_bench_atomics")
     return out.value
+
+
+def image_gradient(image, filter_size):
+    """imageGradient (RendererUtil.h:566-620) of [..., H, W, 3] fp32 CUDA images -> (dI/du, dI/dv)."""
+    image = image.contiguous().float()
+    H, W = int(image.shape[-3]), int(image.shape[-2])
+    n = image.numel() // (H * W * 3)
+    du, dv = torch.empty_like(image), torch.empty_like(image)
+    with torch.cuda.device(image.device):
+        _check(lib().gvv_image_gradient(image.device.index or 0, n, H, W, int(filter_size), _ptr(image), _ptr(du), _ptr(dv),
+                                        ctypes.c_void_p(torch.cuda.current_stream(image.device).cuda_stream)), "gvv_image_gradient")
+    return du, dv
+
+
+def gaussian_smooth(image, taps):
+    """Separable depthwise Gaussian (zero SAME padding) of [..., H, W, 3] fp32 CUDA images with the
+    normalised 1-D kernel `taps` (odd length), see GaussianSmoothingGpu.smoothImage."""
+    image = image.contiguous().float()
+    taps = np.ascontiguousarray(taps, dtype=np.float32)
+    if taps.size % 2 != 1:
+        raise GvvError("gaussian_smooth needs an odd number of taps")
+    H, W = int(image.shape[-3]), int(image.shape[-2])
+    n = image.numel() // (H * W * 3)
+    tmp, out = torch.empty_like(image), torch.empty_like(image)
+    with torch.cuda.device(image.device):
+        _check(lib().gvv_gaussian_smooth(image.device.index or 0, n, H, W, taps.size // 2, taps.ctypes.data, _ptr(image), _ptr(tmp), _ptr(out),
+                                         ctypes.c_void_p(torch.cuda.current_stream(image.device).cuda_stream)), "gvv_gaussian_smooth")
+    return out

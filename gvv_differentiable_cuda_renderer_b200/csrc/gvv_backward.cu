@@ -92,13 +92,13 @@ __device__ __forceinline__ void bary_vjp(V3 o, V3 d, V3 v0, V3 v1, V3 v2, float 
 
 struct PixelParams {
   const float *render_grad, *target_grad, *vertex_pos, *vertex_color, *texture, *sh_coeff, *target_image,
-      *vertex_normal, *bary, *texcoords;
+      *vertex_normal, *bary, *texcoords, *target_du, *target_dv;
   const int32_t* face;
   const int4* faces4;
   const CamRec* cams;
   const float4 *pos4, *col4, *nor4;
   float *vpos_grad, *vcol_grad, *tex_grad, *sh_grad, *gnorm;
-  int C, N, W, H, texH, texW, albedo, shading, imgFilter;
+  int C, N, W, H, texH, texW, albedo, shading, imgFilter, texBilinear;
 };
 
 constexpr int kVals = 27;
@@ -140,7 +140,12 @@ __device__ __forceinline__ void bary_vjp_fast(V3 o, V3 d, V3 v0, V3 v1, V3 v2, f
 
 __device__ __forceinline__ V3 ld4(const float4* __restrict__ p, size_t i) { const float4 v = __ldg(p + i); return v3(v.x, v.y, v.z); }
 
-// grid (W/32, H/8, V), 256 threads: warp w owns the 32-pixel scanline segment y = 8*by + w.
+// grid (W/32, H/32, V), 256 threads: the CTA owns a 32x32 pixel tile, warp w the 32-pixel scanline segments
+// y = 32*by + 8*s + w of its four 8-row slabs s.  All four face ids of a thread are loaded up front, so an empty
+// tile (about 40 % of them at 50 % coverage) costs ONE memory round trip and one barrier; the warps then run
+// their segments without any block barrier, and the SH gradient is reduced once per tile.
+constexpr int kSlabs = 4;
+
 __global__ void __launch_bounds__(256, 4)
 pixel_grad_kernel(const PixelParams p) {
   __shared__ __align__(16) float buf[8][kVals * kRow];   // per warp: value-major, kRow floats per value (32 pixels + pad)
@@ -150,28 +155,41 @@ pixel_grad_kernel(const PixelParams p) {
 
   const int view = blockIdx.z, b = view / p.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + warp;
-  const bool inb = x < p.W && y < p.H;
-  const size_t pix = (size_t)view * p.W * p.H + (size_t)y * p.W + x;
-  const int face = inb ? __ldg(p.face + pix) : -1;
-  const bool covered = face >= 0;
+  const int x = blockIdx.x * 32 + lane;
+  const size_t viewBase = (size_t)view * p.W * p.H;
+  bool any = false;
+#pragma unroll
+  for (int s = 0; s < kSlabs; ++s) {
+    const int ys = blockIdx.y * 32 + s * 8 + warp;
+    const int f = (x < p.W && ys < p.H) ? __ldg(p.face + viewBase + (size_t)ys * p.W + x) : -1;
+    any = any || f >= 0;
+  }
   const bool shaded = p.shading == GVV_SHADING_SHADED;
 
-  // camera + SH staging overlaps the latency of the face load; ONE barrier publishes both and
-  // tells whether anything is visible in this 32x8 block
+  // camera + SH staging overlaps the latency of the face loads; ONE barrier publishes both and
+  // tells whether anything is visible in this 32x32 tile
   if (tid < 64) reinterpret_cast<float*>(&cam)[tid] = __ldg(reinterpret_cast<const float*>(p.cams + view) + tid);
   if (tid >= 64 && tid < 64 + 27) shc[tid - 64] = __ldg(p.sh_coeff + (size_t)view * 27 + (tid - 64));
-  if (__syncthreads_or(covered) == 0) return;
+  if (__syncthreads_or(any) == 0) return;
 
   float* mybuf = buf[warp];
   float* mine = mybuf + lane;   // value j of this lane's pixel lives at mine[j * kRow]
+  float shsum = 0.f;            // lane j < 27: SH gradient (ch,k) summed over this warp's segments
+
+#pragma unroll 1
+  for (int slab = 0; slab < kSlabs; ++slab) {
+  const int y = blockIdx.y * 32 + slab * 8 + warp;
+  const size_t pix = viewBase + (size_t)y * p.W + x;
+  const int face = (x < p.W && y < p.H) ? __ldg(p.face + pix) : -1;      // second read of the line: L1/L2 hit
+  const bool covered = face >= 0;
   const unsigned cv = __ballot_sync(FULL_MASK, covered);
+  if (cv == 0) continue;
   float gA[3] = {0.f, 0.f, 0.f};
   float Y[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) Y[k] = 0.f;
 
-  if (cv) {
+  {
     if (covered) {
       // ---- per-pixel setup (CUDABasedRasterizationGrad.cu:205-240) ----
       const F3 rdx = ray_dir_exact(cam.Pinv, cam.ro, (float)x + 0.5f, (float)y + 0.5f);
@@ -224,7 +242,7 @@ pixel_grad_kernel(const PixelParams p) {
         const float LU = (float)(int)(u - 0.5f) + 0.5f, HU = (float)(int)(u - 0.5f) + 1.5f;
         const float LV = (float)(int)(v - 0.5f) + 0.5f, HV = (float)(int)(v - 0.5f) + 1.5f;
         const float* tex = p.texture + (size_t)b * p.texH * p.texW * 3;
-        const int lu = (int)LU, hu = (int)HU, lv = (int)LV, hv = (int)HV;
+        const int lu = (int)LU, hu = min((int)HU, p.texW - 1), lv = (int)LV, hv = min((int)HV, p.texH - 1);   // hu, hv only clamp for 1-texel-wide textures
         // bilinear mix exactly as written in :311-312 (the forward uses the nearest texel)
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
@@ -232,9 +250,22 @@ pixel_grad_kernel(const PixelParams p) {
           const float cHULV = __ldg(tex + 3 * ((size_t)p.texW * lv + hu) + ch), cHUHV = __ldg(tex + 3 * ((size_t)p.texW * hv + hu) + ch);
           alb[ch] = (v - LV) * ((u - LU) * cLULV + (HU - u) * cHULV) + (HV - v) * ((u - LU) * cLUHV + (HU - u) * cHUHV);
         }
-        if (!flipped) {   // unweighted add to texel (LV,LU) (:382-384)
-          float* tg = p.tex_grad + ((size_t)b * p.texH * p.texW + (size_t)p.texW * lv + lu) * 3;
-          atomicAdd(tg + 0, gl[0]); atomicAdd(tg + 1, gl[1]); atomicAdd(tg + 2, gl[2]);
+        if (!flipped) {
+          float* tgb = p.tex_grad + (size_t)b * p.texH * p.texW * 3;
+          if (p.texBilinear) {
+            // non-default variant: the four weighted adds the reference has commented out (:361-378), weights as written there
+            const float wLULV = (v - LV) * (u - LU), wLUHV = (HV - v) * (u - LU), wHULV = (v - LV) * (HU - u), wHUHV = (HV - v) * (HU - u);
+            float* t0 = tgb + ((size_t)p.texW * lv + lu) * 3; float* t1 = tgb + ((size_t)p.texW * hv + lu) * 3;
+            float* t2 = tgb + ((size_t)p.texW * lv + hu) * 3; float* t3 = tgb + ((size_t)p.texW * hv + hu) * 3;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+              atomicAdd(t0 + ch, gl[ch] * wLULV); atomicAdd(t1 + ch, gl[ch] * wLUHV);
+              atomicAdd(t2 + ch, gl[ch] * wHULV); atomicAdd(t3 + ch, gl[ch] * wHUHV);
+            }
+          } else {          // unweighted add to texel (LV,LU) (:382-384)
+            float* tg = tgb + ((size_t)p.texW * lv + lu) * 3;
+            atomicAdd(tg + 0, gl[0]); atomicAdd(tg + 1, gl[1]); atomicAdd(tg + 2, gl[2]);
+          }
         }
       }
       gA[0] = g.x * alb[0]; gA[1] = g.y * alb[1]; gA[2] = g.z * alb[2];
@@ -272,7 +303,9 @@ pixel_grad_kernel(const PixelParams p) {
       if (p.target_grad) {
         const int fs = p.imgFilter;
         V3 dIu = v3(0.f, 0.f, 0.f), dIv = v3(0.f, 0.f, 0.f);
-        if (x >= fs + 1 && y >= fs + 1 && x < p.W - (fs + 1) && y < p.H - (fs + 1)) {   // imageGradient, RendererUtil.h:566-620
+        if (p.target_du) {            // precomputed once per target (gvv_image_gradient + gvv_set_target_gradient)
+          dIu = ldv3(p.target_du, pix); dIv = ldv3(p.target_dv, pix);
+        } else if (x >= fs + 1 && y >= fs + 1 && x < p.W - (fs + 1) && y < p.H - (fs + 1)) {   // imageGradient, RendererUtil.h:566-620
           const float* img = p.target_image + (size_t)view * p.W * p.H * 3;
           float norm = 0.f;
           for (int yy = -fs; yy <= fs; ++yy)
@@ -354,9 +387,8 @@ pixel_grad_kernel(const PixelParams p) {
   }
 
   // ---- SH gradient: 12 values per pixel (g*albedo, Y) stored value-major; lane j = (ch,k) sums
-  // gA[ch]*Y[k] over the 32 pixels with float4 reads (uncovered pixels store zeros); warp -> block -> 27 atomics ----
-  float shsum = 0.f;
-  if (shaded && cv) {
+  // gA[ch]*Y[k] over the 32 pixels with float4 reads (uncovered pixels store zeros) ----
+  if (shaded) {
     mine[0 * kRow] = gA[0]; mine[1 * kRow] = gA[1]; mine[2 * kRow] = gA[2];   // zeros where not covered
 #pragma unroll
     for (int k = 0; k < 9; ++k) mine[(3 + k) * kRow] = Y[k];
@@ -370,7 +402,11 @@ pixel_grad_kernel(const PixelParams p) {
         shsum = fmaf(a4.x, y4.x, fmaf(a4.y, y4.y, fmaf(a4.z, y4.z, fmaf(a4.w, y4.w, shsum))));
       }
     }
+    __syncwarp();
   }
+  }   // slab
+
+  // warp -> block -> 27 atomics per tile
   if (lane < kVals) shPart[warp][lane] = shsum;
   __syncthreads();
   if (shaded && tid < kVals) {
@@ -474,13 +510,13 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   PixelParams p;
   p.render_grad = a.render_grad; p.target_grad = a.target_grad; p.vertex_pos = a.vertex_pos; p.vertex_color = a.vertex_color;
   p.texture = a.texture; p.sh_coeff = a.sh_coeff; p.target_image = a.target_image; p.vertex_normal = a.vertex_normal;
-  p.bary = a.bary; p.texcoords = a.texcoords; p.face = a.face; p.faces4 = a.faces4; p.cams = a.s.cams;
+  p.bary = a.bary; p.texcoords = a.texcoords; p.target_du = a.target_du; p.target_dv = a.target_dv; p.face = a.face; p.faces4 = a.faces4; p.cams = a.s.cams;
   p.pos4 = a.s.bpos4; p.col4 = a.s.bcol4; p.nor4 = a.s.bnor4;
   p.vpos_grad = a.vpos_grad; p.vcol_grad = a.vcol_grad; p.tex_grad = a.tex_grad; p.sh_grad = a.sh_grad; p.gnorm = a.s.gnorm;
   p.C = a.C; p.N = a.N; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
-  p.albedo = a.albedo; p.shading = a.shading; p.imgFilter = a.imgFilter;
+  p.albedo = a.albedo; p.shading = a.shading; p.imgFilter = a.imgFilter; p.texBilinear = a.texBilinear;
   tm->begin(K_PIXEL_GRAD, st);
-  pixel_grad_kernel<<<dim3((a.W + 31) / 32, (a.H + 7) / 8, V), 256, 0, st>>>(p);
+  pixel_grad_kernel<<<dim3((a.W + 31) / 32, (a.H + 31) / 32, V), 256, 0, st>>>(p);
   tm->end(st);
   ++launches;
   if (a.shading == GVV_SHADING_SHADED) {

@@ -404,7 +404,7 @@ struct RasterParams {
   const float* texture; const float* texcoords; const float* sh_coeff;
   float* bary; int32_t* face; float* render;
   unsigned long long* ctaTrace;
-  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, spanZ, role;
+  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, spanZ, role, texBilinear;
   float cullMargin;
 };
 
@@ -842,8 +842,22 @@ raster_kernel(const RasterParams p) {
         // nearest texel (LU,LV); the bilinear mix is commented out in the reference (:372-373)
         const int iu = __float2int_rz(__fadd_rn((float)__float2int_rz(__fadd_rn(fu, -0.5f)), 0.5f));
         const int iv = __float2int_rz(__fadd_rn((float)__float2int_rz(__fadd_rn(fv, -0.5f)), 0.5f));
-        const float* tx = p.texture + ((size_t)b * p.texH * p.texW + (size_t)iv * p.texW + iu) * 3;
+        const float* tb = p.texture + (size_t)b * p.texH * p.texW * 3;
+        const float* tx = tb + ((size_t)iv * p.texW + iu) * 3;
         cr = __ldg(tx); cg = __ldg(tx + 1); cb = __ldg(tx + 2);
+        if (p.texBilinear) {
+          // non-default variant: the bilinear mix the reference has commented out (:365-372), weights as written there
+          const float LU = __fadd_rn((float)__float2int_rz(__fadd_rn(fu, -0.5f)), 0.5f), HU = __fadd_rn((float)__float2int_rz(__fadd_rn(fu, -0.5f)), 1.5f);
+          const float LV = __fadd_rn((float)__float2int_rz(__fadd_rn(fv, -0.5f)), 0.5f), HV = __fadd_rn((float)__float2int_rz(__fadd_rn(fv, -0.5f)), 1.5f);
+          const int hu = min(__float2int_rz(HU), p.texW - 1), hv = min(__float2int_rz(HV), p.texH - 1);
+          const float wLULV = (fv - LV) * (fu - LU), wLUHV = (HV - fv) * (fu - LU), wHULV = (fv - LV) * (HU - fu), wHUHV = (HV - fv) * (HU - fu);
+          const float* tLUHV = tb + ((size_t)hv * p.texW + iu) * 3;
+          const float* tHULV = tb + ((size_t)iv * p.texW + hu) * 3;
+          const float* tHUHV = tb + ((size_t)hv * p.texW + hu) * 3;
+          cr = wLULV * cr + wHULV * __ldg(tHULV) + wLUHV * __ldg(tLUHV) + wHUHV * __ldg(tHUHV);
+          cg = wLULV * cg + wHULV * __ldg(tHULV + 1) + wLUHV * __ldg(tLUHV + 1) + wHUHV * __ldg(tHUHV + 1);
+          cb = wLULV * cb + wHULV * __ldg(tHULV + 2) + wLUHV * __ldg(tLUHV + 2) + wHUHV * __ldg(tHUHV + 2);
+        }
       } else if (p.albedo == GVV_ALBEDO_VERTEX_COLOR) {
         const float4 c0 = __ldg(vc + fc.x), c1 = __ldg(vc + fc.y), c2 = __ldg(vc + fc.z);
         cr = interp3(a, bq, c, c0.x, c1.x, c2.x);
@@ -972,7 +986,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   p.texture = a.texture; p.texcoords = a.texcoords; p.sh_coeff = a.sh_coeff;
   p.bary = a.bary; p.face = a.face; p.render = a.render; p.ctaTrace = a.s.ctaTrace;
   p.C = a.C; p.N = a.N; p.F = a.F; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
-  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv; p.interleave = a.interleave; p.hiz = a.hiz; p.spanZ = a.spanZ;
+  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv; p.interleave = a.interleave; p.hiz = a.hiz; p.spanZ = a.spanZ; p.texBilinear = a.texBilinear;
   const dim3 gridT((unsigned)nItems * (unsigned)V);
   tm->begin(K_RASTER, st);
   static bool attrSet = false;

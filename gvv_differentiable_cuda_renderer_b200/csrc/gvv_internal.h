@@ -60,6 +60,8 @@ struct gvv_renderer {
   int F = 0, N = 0, C = 0, W = 0, H = 0;
   int albedo = 0, shading = 0, imgFilter = 1, texFilter = 1, computeNormalMap = 0;
   int tile = 32, tilesX = 0, tilesY = 0, nT = 0;
+  const float* targetDu = nullptr; const float* targetDv = nullptr;   // caller-owned precomputed target-image gradient (gvv_set_target_gradient)
+  int texBilinear = 0;        // non-default: bilinear texture fetch + weighted 4-texel gradient scatter (the variants the reference has commented out)
   int spreadEmpty = 0;        // raster: interleave the (HBM-bound) empty tiles with the (ALU-bound) non-empty ones
   int heavyThr = 0;         // raster: bins of >= heavyThr triangles are rasterised by 1024-thread CTAs on a side stream; 0 = off
   cudaStream_t sideStream = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr;
@@ -88,7 +90,7 @@ namespace gvv {
 
 struct FwdArgs {
   int B, C, N, F, W, H, texH, texW, albedo, shading;
-  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, spanZ, splitUnit, heavyThr, spreadEmpty;
+  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, spanZ, splitUnit, heavyThr, spreadEmpty, texBilinear;
   cudaStream_t sideStream; cudaEvent_t evFork, evJoin;
   float cullMargin;
   const float *vertex_pos, *vertex_color, *texture, *sh_coeff, *extrinsics, *intrinsics;
@@ -100,9 +102,9 @@ struct FwdArgs {
 };
 
 struct BwdArgs {
-  int B, C, N, F, W, H, texH, texW, albedo, shading, imgFilter;
+  int B, C, N, F, W, H, texH, texW, albedo, shading, imgFilter, texBilinear;
   const float *render_grad, *target_grad, *vertex_pos, *vertex_color, *texture, *sh_coeff, *target_image,
-      *vertex_normal, *bary, *extrinsics, *intrinsics, *texcoords;
+      *vertex_normal, *bary, *extrinsics, *intrinsics, *texcoords, *target_du, *target_dv;
   const int32_t* face;
   const int4* faces4;
   const int *vfOffsets, *vfList;

@@ -93,12 +93,12 @@ def base_sh():
 
 
 def make_scene(kind="sphere", rings=24, segments=32, cameras=2, width=128, height=128, batch=1, tex=64, seed=0,
-               coverage_radius_frac=0.4, distance=1500.0):
+               coverage_radius_frac=0.4, distance=1500.0, noise=0.02):
     """A complete set of op inputs (numpy, op layout).  `coverage_radius_frac` = silhouette
     radius / image width for the sphere (0.4 -> ~50 % coverage, the headline workload)."""
     rng = np.random.default_rng(seed + 1)
     if kind == "sphere":
-        verts, faces, tcs = uv_sphere(rings, segments, seed=seed)
+        verts, faces, tcs = uv_sphere(rings, segments, noise=noise, seed=seed)
         radius = 150.0
     elif kind == "pyramid":
         verts, faces, tcs = pyramid()

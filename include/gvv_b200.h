@@ -117,6 +117,28 @@ int gvv_backward(gvv_handle h, int32_t batch, int32_t tex_h, int32_t tex_w,
 
 const char* gvv_last_error(void);
 
+/* ---- loss-side helpers next to the op; no handle needed ----------------- */
+
+/* smoothImage (python/utils/GaussianSmoothingGpu.py:12-37): depthwise Gaussian over `images` dense
+ * [height,width,3] fp32 images with zero "SAME" padding, as two separable passes.  taps: HOST
+ * float[2*half_size+1], the normalised 1-D kernel (the reference's 2-D kernel is outer(vals,vals)/sum);
+ * in/tmp/out: DEVICE buffers of images*height*width*3 floats (tmp is scratch; out may alias in, not tmp).
+ * Cross-correlation like tf.nn.depthwise_conv2d, so the adjoint is the same call with reversed taps. */
+int gvv_gaussian_smooth(int32_t device, int64_t images, int32_t height, int32_t width, int32_t half_size,
+                        const float* taps, const float* in, float* tmp, float* out, void* stream);
+
+/* imageGradient (cpp/src/Utils/RendererUtil.h:566-620) of `images` dense [height,width,3] images:
+ * d_du, d_dv (DEVICE, same shape) = dI/du and dI/dv, zero within filter_size+1 pixels of the border.
+ * The backward evaluates exactly this per covered pixel on every call when target_buffer_grad is
+ * given; for a constant target, compute it once and pass it with gvv_set_target_gradient. */
+int gvv_image_gradient(int32_t device, int64_t images, int32_t height, int32_t width, int32_t filter_size,
+                       const float* image, float* d_du, float* d_dv, void* stream);
+
+/* Caller-owned precomputed target-image gradient [B,C,H,W,3] x 2 for the model-to-data term of
+ * gvv_backward (must match the handle's image_filter_size and the target passed to gvv_backward);
+ * NULL, NULL = recompute per pixel like the reference (default). */
+int gvv_set_target_gradient(gvv_handle h, const float* d_du, const float* d_dv);
+
 /* ---- diagnostics (not part of the reference boundary) ------------------------------------ */
 
 /* Number of kernels the library launched on behalf of this handle since creation. */
@@ -137,7 +159,10 @@ int gvv_debug_eval(gvv_handle h, int32_t n, const int32_t* queries, int32_t* out
 /* Runtime knobs: key "tile" (16|32 rasteriser tile edge; default 32); key "cull_margin_milli" (fixed
  * part, in 1/1000 pixel, of the margin of the conservative screen-space pre-test that decides which
  * bbox pixels get the exact test; default 62 (1/16 px); negative = test every bbox pixel exactly, like the
- * reference -- results are identical either way, see tests); key "time_kernels" (1: record
+ * reference -- results are identical either way, see tests); key "texture_bilinear" (1: the bilinear
+ * texture fetch and the weighted 4-texel texture-gradient scatter the reference has commented out,
+ * CUDABasedRasterization.cu:365-372, CUDABasedRasterizationGrad.cu:361-378; default 0 = reference
+ * behaviour: nearest texel, unweighted add); key "time_kernels" (1: record
  * a CUDA-event pair around every kernel on the launching stream, 0: off; either resets the log).
  * Returns 0 on success. */
 int gvv_set_option(gvv_handle h, const char* key, int32_t value);

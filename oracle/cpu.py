@@ -38,6 +38,11 @@ def _load():
     return _lib
 
 
+def set_texture_bilinear(on):
+    """Non-default variant: bilinear texture fetch + weighted 4-texel gradient scatter (commented out in the reference)."""
+    _load().gvvo_set_texture_bilinear(int(bool(on)))
+
+
 def max_threads():
     return int(_load().gvvo_max_threads())
 

@@ -171,6 +171,10 @@ struct Mesh {
   }
 };
 
+// Non-default variant (gvvo_set_texture_bilinear): the bilinear texture fetch (CUDABasedRasterization.cu:365-372)
+// and the four weighted gradient adds (CUDABasedRasterizationGrad.cu:361-378) that the reference has commented out.
+static int g_texBilinear = 0;
+
 struct TexSample { float u, v; int lu, lv, hu, hv; float LU, LV, HU, HV; };
 // texture coordinate -> texel (CUDABasedRasterization.cu:326-345, CUDABasedRasterizationGrad.cu:250-289)
 TexSample tex_coord(const float* tc, int face, V3 abc, int texW, int texH) {
@@ -184,13 +188,15 @@ TexSample tex_coord(const float* tc, int face, V3 abc, int texW, int texH) {
   s.u = u; s.v = v;
   s.LU = (float)(int)(u - 0.5f) + 0.5f; s.HU = (float)(int)(u - 0.5f) + 1.5f;
   s.LV = (float)(int)(v - 0.5f) + 0.5f; s.HV = (float)(int)(v - 0.5f) + 1.5f;
-  s.lu = (int)s.LU; s.hu = (int)s.HU; s.lv = (int)s.LV; s.hv = (int)s.HV;
+  s.lu = (int)s.LU; s.hu = std::min((int)s.HU, texW - 1); s.lv = (int)s.LV; s.hv = std::min((int)s.HV, texH - 1);   // clamps only act on 1-texel-wide textures
   return s;
 }
 
 }  // namespace
 
 extern "C" {
+
+void gvvo_set_texture_bilinear(int on) { g_texBilinear = on ? 1 : 0; }
 
 // Forward of the op for all batch elements (CudaRenderer.cpp:298-335 -> renderBuffersGPU,
 // CUDABasedRasterization.cu:449-473).  Extra outputs (may be null): best_depth / second_depth
@@ -294,7 +300,14 @@ long long gvvo_forward(const int* faces, int F, const float* texcoords, int N, i
               V3 col = {0.f, 0.f, 0.f};
               if (albedo == Textured) {                                                    // :324-374 (nearest texel)
                 const TexSample s = tex_coord(texcoords, f, abc, texW, texH);
-                col = ld3(texture + (long)b * texH * texW * 3, (long)texW * s.lv + s.lu);
+                const float* tb = texture + (long)b * texH * texW * 3;
+                col = ld3(tb, (long)texW * s.lv + s.lu);
+                if (g_texBilinear) {
+                  const float wLULV = (s.v - s.LV) * (s.u - s.LU), wLUHV = (s.HV - s.v) * (s.u - s.LU);
+                  const float wHULV = (s.v - s.LV) * (s.HU - s.u), wHUHV = (s.HV - s.v) * (s.HU - s.u);
+                  col = wLULV * col + wHULV * ld3(tb, (long)texW * s.lv + s.hu) + wLUHV * ld3(tb, (long)texW * s.hv + s.lu) +
+                        wHUHV * ld3(tb, (long)texW * s.hv + s.hu);
+                }
               } else if (albedo == VertexColor) {                                          // :375-381
                 const float* vc = vertex_color + (long)b * N * 3;
                 col = ld3(vc, i0) * abc.x + ld3(vc, i1) * abc.y + ld3(vc, i2) * abc.z;
@@ -398,8 +411,14 @@ int gvvo_backward(const int* faces, int F, const float* texcoords, int N, int C,
           if (albedo == VertexColor) {                                                       // :334-342
             for (int i = 0; i < 3; ++i) for (int ch = 0; ch < 3; ++ch) GC[3 * (size_t)id[i] + ch] += (double)(gl[ch] * bc[i]);
           } else if (albedo == Textured && !flipped) {                                       // :343-385
-            double* GT = gt[t].data() + ((size_t)texW * ts.lv + ts.lu) * 3;
-            GT[0] += gl[0]; GT[1] += gl[1]; GT[2] += gl[2];
+            if (g_texBilinear) {
+              const float w4[4] = {(ts.v - ts.LV) * (ts.u - ts.LU), (ts.HV - ts.v) * (ts.u - ts.LU), (ts.v - ts.LV) * (ts.HU - ts.u), (ts.HV - ts.v) * (ts.HU - ts.u)};
+              const size_t t4[4] = {(size_t)texW * ts.lv + ts.lu, (size_t)texW * ts.hv + ts.lu, (size_t)texW * ts.lv + ts.hu, (size_t)texW * ts.hv + ts.hu};
+              for (int k = 0; k < 4; ++k) for (int ch = 0; ch < 3; ++ch) gt[t][t4[k] * 3 + ch] += (double)(gl[ch] * w4[k]);
+            } else {
+              double* GT = gt[t].data() + ((size_t)texW * ts.lv + ts.lu) * 3;
+              GT[0] += gl[0]; GT[1] += gl[1]; GT[2] += gl[2];
+            }
           }
           const float gA[3] = {g.x * alb.x, g.y * alb.y, g.z * alb.z};                       // GVCB * JCoLi
           if (shading == Shaded) {                                                           // :402-436

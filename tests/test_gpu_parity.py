@@ -364,3 +364,59 @@ def test_edge_cases():
     r.close()
     with pytest.raises(_native.GvvError):
         _native.NativeRenderer(faces, None, 6, 1, 8, 8, "textured", "shaded", device=dev())
+
+
+def test_bilinear_texture_variant():
+    """texture_bilinear = 1 (non-default): the bilinear fetch (CUDABasedRasterization.cu:365-372) and the four
+    weighted texture-gradient adds (CUDABasedRasterizationGrad.cu:361-378) the reference has commented out.
+    Checked against Oracle 2 with the same switch, by finite differences (the texture is a linear input and the
+    scatter is now the exact adjoint of the fetch) and by the weights summing to one."""
+    from oracle import cpu
+    sc = synthetic.make_scene(kind="sphere", rings=14, segments=18, cameras=2, width=72, height=64, tex=20, seed=5, noise=0.0)
+    N, C, W, H = sc["num_vertices"], sc["num_cameras"], sc["width"], sc["height"]
+    ins = [T(sc[k]) for k in INPUT_KEYS]
+    r = make(sc, "textured", "shaded")
+    bary0, face0, render0, vn0, _, _ = r.forward(*ins)
+    rg = torch.randn(render0.shape, generator=torch.Generator().manual_seed(1)).to(dev())
+    g_nearest = r.backward(rg, None, ins[0], ins[1], ins[2], ins[3], ins[4], vn0, bary0, face0, ins[5], ins[6])
+    r.set_option("texture_bilinear", 1)
+    bary, face, render, vn, _, _ = r.forward(*ins)
+    assert torch.equal(face, face0) and torch.equal(bary, bary0)          # visibility does not depend on the texture filter
+    assert not torch.equal(render, render0)
+    g_bil = r.backward(rg, None, ins[0], ins[1], ins[2], ins[3], ins[4], vn, bary, face, ins[5], ins[6])
+    # (a) oracle with the same switch
+    cpu.set_texture_bilinear(True)
+    try:
+        o = cpu.forward(sc["faces"], sc["texcoords"], N, C, W, H, "textured", "shaded", sc["vertex_pos"], sc["vertex_color"],
+                        sc["texture"], sc["sh_coeff"], sc["extrinsics"], sc["intrinsics"])
+        f = face.cpu().numpy()
+        same = (f == o["face"]) & (f >= 0)
+        assert same.sum() > 0.95 * (f >= 0).sum()
+        assert np.abs(render.cpu().numpy() - o["render"])[same].max() <= 5e-4
+        go = cpu.backward(sc["faces"], sc["texcoords"], N, C, W, H, "textured", "shaded", 1, rg.cpu().numpy(), None, sc["vertex_pos"],
+                          sc["vertex_color"], sc["texture"], sc["sh_coeff"], sc["target_image"], vn.cpu().numpy(), bary.cpu().numpy(), f,
+                          sc["extrinsics"], sc["intrinsics"])
+    finally:
+        cpu.set_texture_bilinear(False)
+    grads_close(g_bil, go)
+    # (b) the four weights sum to one: the same total lands in the texture gradient as with the nearest-texel add
+    tot_b, tot_n = g_bil[2].double().sum((0, 1, 2)), g_nearest[2].double().sum((0, 1, 2))
+    assert torch.allclose(tot_b, tot_n, rtol=1e-4, atol=1e-3), (tot_b, tot_n)
+    # (c) finite differences along a random texture direction (fp64 accumulation of the loss).  The reference
+    # skips the texture gradient where the shading normal was flipped (grazing pixels at the silhouette,
+    # CUDABasedRasterizationGrad.cu:345), so the loss only looks at the central disc of the sphere.
+    yy, xx = np.mgrid[0:H, 0:W]
+    disc = ((xx - W / 2) ** 2 + (yy - H / 2) ** 2) <= (0.6 * 0.4 * W) ** 2
+    rgc = rg * T(disc.astype(np.float32))[None, None, :, :, None]
+    g_c = r.backward(rgc, None, ins[0], ins[1], ins[2], ins[3], ins[4], vn, bary, face, ins[5], ins[6])
+    D = torch.randn(ins[2].shape, generator=torch.Generator().manual_seed(2)).to(dev())
+
+    def loss(tex):
+        a = list(ins); a[2] = tex
+        return float((r.forward(*a)[2].double() * rgc.double()).sum())
+
+    eps = 1e-2
+    fd = (loss(ins[2] + eps * D) - loss(ins[2] - eps * D)) / (2 * eps)
+    an = float((g_c[2].double() * D.double()).sum())
+    assert abs(an) > 1.0 and abs(fd - an) <= 2e-3 * abs(an) + 1e-3, (fd, an)
+    r.close()
