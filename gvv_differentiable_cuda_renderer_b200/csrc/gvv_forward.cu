@@ -1000,7 +1000,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   // Heavy bins (>= heavyThr triangles among the kHeavySlots heaviest items of a view) get a 1024-thread CTA, i.e.
   // a whole SM, from a second launch on a side stream: a 256-thread CTA shares its SM with three others and
   // would make the tile the critical path of the launch (measured: 236 us of a 274 us launch).
-  constexpr int kHeavySlots = 32;
+  const int kHeavySlots = nItems < 32 ? nItems : 32;
   const bool useHeavy = a.heavyThr > 0 && a.tile == 32 && !a.rayCache && a.ctaThreads == 256 && a.sideStream != nullptr;
   const int maxLog = a.splitUnit > 0 ? (a.tile == 32 ? 3 : 2) : 0;
   bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.nT, nItems, a.splitUnit > 0 ? a.splitUnit : 1, maxLog,

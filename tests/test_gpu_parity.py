@@ -420,3 +420,34 @@ def test_bilinear_texture_variant():
     an = float((g_c[2].double() * D.double()).sum())
     assert abs(an) > 1.0 and abs(fd - an) <= 2e-3 * abs(an) + 1e-3, (fd, an)
     r.close()
+
+
+def test_forward_backward_are_cuda_graph_capturable():
+    """Steady-state gvv_forward / gvv_backward never allocate or synchronise (include/gvv_b200.h), so one
+    fwd+bwd step can be captured in a CUDA graph and replayed: same bits in the integer/forward outputs,
+    gradients equal up to atomic order."""
+    sc = synthetic.make_scene(kind="sphere", rings=24, segments=30, cameras=2, width=160, height=128, tex=16, seed=6)
+    r = make(sc, "vertexColor", "shaded")
+    ins = [T(sc[k]) for k in INPUT_KEYS]
+    rg = torch.randn((1, sc["num_cameras"], sc["height"], sc["width"], 3), generator=torch.Generator().manual_seed(0)).to(dev())
+    bary0, face0, render0, vn0, _, _ = r.forward(*ins)                       # eager: also sizes the scratch
+    g0 = r.backward(rg, None, ins[0], ins[1], ins[2], ins[3], ins[4], vn0, bary0, face0, ins[5], ins[6])
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        bary, face, render, vn, _, _ = r.forward(*ins)
+        g = r.backward(rg, None, ins[0], ins[1], ins[2], ins[3], ins[4], vn, bary, face, ins[5], ins[6])
+    for _ in range(3):
+        face.fill_(-7); render.zero_(); g[0].fill_(123.0)
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(face, face0) and torch.equal(bary.view(torch.int32), bary0.view(torch.int32))
+    assert torch.equal(render.view(torch.int32), render0.view(torch.int32)) and torch.equal(vn, vn0)
+    grads_close(g, g0, rel=1e-5)
+    # the inputs are read at replay time: new colours -> new image, same visibility
+    ins[1].mul_(0.5)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(face, face0) and not torch.equal(render, render0)
+    del graph
+    r.close()
