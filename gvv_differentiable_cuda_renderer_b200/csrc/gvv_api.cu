@@ -123,6 +123,7 @@ extern "C" int gvv_create(const gvv_desc* d, gvv_handle* out) {
   h->texFilter = d->texture_filter_size;
   h->computeNormalMap = d->compute_normal_map ? 1 : 0;
   set_tile(h, 32);
+  { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device) == cudaSuccess && sms > 0) h->ctaSlots = 4 * sms; }
   // side stream + fork/join events of the heavy-tile raster launch (gvv_forward.cu); failure just disables that path
   if (cudaStreamCreateWithFlags(&h->sideStream, cudaStreamNonBlocking) != cudaSuccess) h->sideStream = nullptr;
   if (cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming) != cudaSuccess) {
@@ -209,6 +210,7 @@ extern "C" int gvv_set_option(gvv_handle h, const char* key, int32_t value) {
   if (!strcmp(key, "cta_trace")) { cudaSetDevice(h->device); cudaDeviceSynchronize(); free_scratch(h->s); h->ctaTrace = value ? 1 : 0; return GVV_OK; }   // scratch is re-allocated by the next call
   if (!strcmp(key, "texture_bilinear")) { h->texBilinear = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "spread_empty")) { h->spreadEmpty = value ? 1 : 0; return GVV_OK; }
+  if (!strcmp(key, "heavy_mode")) { if (value < 0 || value > 2) return fail(GVV_EINVAL, "heavy_mode must be 0 (never), 1 (adaptive) or 2 (always)"); h->heavyMode = value; return GVV_OK; }
   if (!strcmp(key, "heavy_thr")) { if (value < 0) return fail(GVV_EINVAL, "heavy_thr must be >= 0"); h->heavyThr = value; return GVV_OK; }
   if (!strcmp(key, "split_unit")) { if (value < 0) return fail(GVV_EINVAL, "split_unit must be >= 0"); h->splitUnit = value; return GVV_OK; }
   if (!strcmp(key, "hiz")) { h->hiz = value ? 1 : 0; return GVV_OK; }
@@ -254,7 +256,7 @@ extern "C" int gvv_forward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
   FwdArgs a;
   a.B = B; a.C = h->C; a.N = h->N; a.F = h->F; a.W = h->W; a.H = h->H; a.texH = texH; a.texW = texW;
   a.albedo = h->albedo; a.shading = h->shading;
-  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin; a.rayCache = h->rayCache; a.batchDiv = h->batchDiv; a.ctaThreads = h->ctaThreads; a.interleave = h->interleave; a.hiz = h->hiz; a.spanZ = h->spanZ; a.splitUnit = h->splitUnit; a.heavyThr = h->heavyThr; a.spreadEmpty = h->spreadEmpty; a.texBilinear = h->texBilinear; a.sideStream = h->sideStream; a.evFork = h->evFork; a.evJoin = h->evJoin;
+  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin; a.rayCache = h->rayCache; a.batchDiv = h->batchDiv; a.ctaThreads = h->ctaThreads; a.interleave = h->interleave; a.hiz = h->hiz; a.spanZ = h->spanZ; a.splitUnit = h->splitUnit; a.heavyThr = h->heavyThr; a.heavyMode = h->heavyMode; a.ctaSlots = h->ctaSlots; a.spreadEmpty = h->spreadEmpty; a.texBilinear = h->texBilinear; a.sideStream = h->sideStream; a.evFork = h->evFork; a.evJoin = h->evJoin;
   a.vertex_pos = vertex_pos; a.vertex_color = vertex_color; a.texture = texture; a.sh_coeff = sh_coeff;
   a.extrinsics = extrinsics; a.intrinsics = intrinsics; a.texcoords = h->texcoords;
   a.faces4 = h->faces4; a.vfOffsets = h->vfOffsets; a.vfList = h->vfList;

@@ -204,7 +204,7 @@ __device__ __forceinline__ int strip_log2(int cnt, int unit, int maxLog) {
 
 __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ tileCount, int* __restrict__ tileOffset,
                                                         int* __restrict__ tileOrder, int nT, int nItems, int splitUnit, int maxLog,
-                                                        int heavyThr, int heavySlots, int spreadEmpty,
+                                                        int heavyThr, int heavySlots, int heavyLoad, int spreadEmpty,
                                                         const float* __restrict__ extr, const float* __restrict__ intr,
                                                         CamRec* __restrict__ cams) {
   __shared__ int warpSum[32];
@@ -283,7 +283,10 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
         else { const int j = pos - n1; pos = j + min(n1, (int)((((long long)(j + 1)) * n1 + n0 - 1) / n0)); }
       }
       // bit 28: the item is rasterised by the 1024-thread launch (one whole SM per tile) instead of a 256-thread CTA
-      const int heavy = (heavyThr > 0 && w >= heavyThr && pos < heavySlots) ? (1 << 28) : 0;
+      // ... when it would otherwise be the critical path of the launch: its bin is more than 1.4x the average
+      // load of a 256-thread CTA slot (heavyLoad = slots / views, carry = bin entries of this view; heavyLoad < 0: always)
+      const bool critical = heavyLoad < 0 || 5ll * w * heavyLoad > 7ll * carry;
+      const int heavy = (heavyThr > 0 && w >= heavyThr && pos < heavySlots && critical) ? (1 << 28) : 0;
       order[pos] = i | (sidx << 20) | (l << 24) | heavy;
     }
   }
@@ -1001,10 +1004,10 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   // a whole SM, from a second launch on a side stream: a 256-thread CTA shares its SM with three others and
   // would make the tile the critical path of the launch (measured: 236 us of a 274 us launch).
   const int kHeavySlots = nItems < 32 ? nItems : 32;
-  const bool useHeavy = a.heavyThr > 0 && a.tile == 32 && !a.rayCache && a.ctaThreads == 256 && a.sideStream != nullptr;
+  const bool useHeavy = a.heavyMode > 0 && a.heavyThr > 0 && a.tile == 32 && !a.rayCache && a.ctaThreads == 256 && a.sideStream != nullptr;
   const int maxLog = a.splitUnit > 0 ? (a.tile == 32 ? 3 : 2) : 0;
   bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.nT, nItems, a.splitUnit > 0 ? a.splitUnit : 1, maxLog,
-                                      useHeavy ? a.heavyThr : 0, kHeavySlots, a.spreadEmpty, a.extrinsics, a.intrinsics, a.s.cams);
+                                      useHeavy ? a.heavyThr : 0, kHeavySlots, a.heavyMode == 2 ? -1 : max(1, a.ctaSlots / V), a.spreadEmpty, a.extrinsics, a.intrinsics, a.s.cams);
   tm->end(st);
   ++launches;
   tm->begin(K_BIN_FILL, st);

@@ -63,7 +63,9 @@ struct gvv_renderer {
   const float* targetDu = nullptr; const float* targetDv = nullptr;   // caller-owned precomputed target-image gradient (gvv_set_target_gradient)
   int texBilinear = 0;        // non-default: bilinear texture fetch + weighted 4-texel gradient scatter (the variants the reference has commented out)
   int spreadEmpty = 0;        // raster: interleave the (HBM-bound) empty tiles with the (ALU-bound) non-empty ones
-  int heavyThr = 0;         // raster: bins of >= heavyThr triangles are rasterised by 1024-thread CTAs on a side stream; 0 = off
+  int heavyMode = 1;          // 0 = never, 1 = only where such a bin would be the critical path of the launch (decided on the GPU), 2 = always
+  int ctaSlots = 592;         // resident 256-thread raster CTAs of the device (4 per SM), set at create
+  int heavyThr = 768;         // raster: bins of >= heavyThr triangles are rasterised by 1024-thread CTAs on a side stream; 0 = off
   cudaStream_t sideStream = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr;
   int splitUnit = 0;          // raster: a bin of >= splitUnit (2x, 4x) triangles is cut into 2 (4, 8) strips with a CTA each; 0 = never (measured slower: every strip re-scans the bin)
   int ctaTrace = 0;           // debug: record per-CTA start/end times of the raster kernel
@@ -90,7 +92,7 @@ namespace gvv {
 
 struct FwdArgs {
   int B, C, N, F, W, H, texH, texW, albedo, shading;
-  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, spanZ, splitUnit, heavyThr, spreadEmpty, texBilinear;
+  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, spanZ, splitUnit, heavyThr, heavyMode, ctaSlots, spreadEmpty, texBilinear;
   cudaStream_t sideStream; cudaEvent_t evFork, evJoin;
   float cullMargin;
   const float *vertex_pos, *vertex_color, *texture, *sh_coeff, *extrinsics, *intrinsics;

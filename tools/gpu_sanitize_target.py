@@ -20,7 +20,7 @@ for kind, kw in (("sphere", dict(rings=16, segments=20, cameras=2, width=100, he
     ins = [T(sc[k]) for k in KEYS]
     B = ins[0].shape[0]
     for albedo, shading in (("vertexColor", "shaded"), ("textured", "shaded"), ("textured", "shadeless"), ("normal", "shaded"), ("foregroundMask", "shaded")):
-        for opts in ({}, {"tile": 16}, {"split_unit": 8, "heavy_thr": 16}, {"texture_bilinear": 1, "cull_margin_milli": -1}, {"span_z": 1, "hiz": 0}):
+        for opts in ({}, {"tile": 16}, {"split_unit": 8, "heavy_thr": 16, "heavy_mode": 2}, {"texture_bilinear": 1, "cull_margin_milli": -1}, {"span_z": 1, "hiz": 0}):
             r = _native.NativeRenderer(sc["faces"], sc["texcoords"], N, C, W, H, albedo, shading, 1, 1, False, dev)
             for k, v in opts.items():
                 r.set_option(k, v)

@@ -12,9 +12,9 @@ N, C, W, H = sc["num_vertices"], 8, 1024, 1024
 ins = [T(sc[k]) for k in ("vertex_pos", "vertex_color", "texture", "sh_coeff", "target_image", "extrinsics", "intrinsics")]
 G = torch.randn((1, C, H, W, 3), generator=torch.Generator().manual_seed(3)).to(dev)
 ref = None
-DEFAULTS = {"tile": 32, "cull_margin_milli": 62, "ray_cache": 0, "batch_div": 8, "cta_threads": 256, "interleave": 1, "hiz": 1, "span_z": 2, "heavy_thr": 0, "spread_empty": 0}
+DEFAULTS = {"tile": 32, "cull_margin_milli": 62, "ray_cache": 0, "batch_div": 8, "cta_threads": 256, "interleave": 1, "hiz": 1, "span_z": 2, "heavy_thr": 768, "heavy_mode": 1, "spread_empty": 0}
 # the first configuration is the reference behaviour: every bbox pixel tested, no depth culling
-configs = [dict(DEFAULTS, cull_margin_milli=-1, hiz=0, span_z=0, heavy_thr=0)]
+configs = [dict(DEFAULTS, cull_margin_milli=-1, hiz=0, span_z=0, heavy_mode=0)]
 for a in sys.argv[1:] or ["", "span_z=0", "hiz=0", "hiz=0,span_z=0"]:     # key=value[,key=value...]
     configs.append(dict(DEFAULTS, **{k: int(v) for k, v in (kv.split("=") for kv in a.split(",") if kv)}))
 for cfg in configs:
