@@ -122,6 +122,9 @@ def run_ours(args, rank, world, local_rank):
     r = _native.NativeRenderer(sc["faces"], sc["texcoords"], N, C, W, H, "vertexColor", "shaded", 1, 1, False, dev)
     if args.tile:
         r.set_option("tile", args.tile)
+    for kv in args.opt:                       # experiments: gvv_set_option knobs, e.g. --opt heavy_mode=0
+        k, v = kv.split("=")
+        r.set_option(k, int(v))
 
     def step():
         bary, face, render, vn, _, _ = r.forward(*ins)
@@ -394,6 +397,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], help="key=value for gvv_set_option (experiments; applies to the resident-input leg)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdarg>
+#include <cstdlib>
+#include <string>
 #include <vector>
 #include <new>
 #include "gvv_internal.h"
@@ -124,13 +126,6 @@ extern "C" int gvv_create(const gvv_desc* d, gvv_handle* out) {
   h->computeNormalMap = d->compute_normal_map ? 1 : 0;
   set_tile(h, 32);
   { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device) == cudaSuccess && sms > 0) h->ctaSlots = 4 * sms; }
-  // side stream + fork/join events of the heavy-tile raster launch (gvv_forward.cu); failure just disables that path
-  if (cudaStreamCreateWithFlags(&h->sideStream, cudaStreamNonBlocking) != cudaSuccess) h->sideStream = nullptr;
-  if (cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming) != cudaSuccess) {
-    if (h->sideStream) cudaStreamDestroy(h->sideStream);
-    h->sideStream = nullptr;
-  }
-  cudaGetLastError();
 
   // topology: faces padded to int4; vertex -> incident faces CSR by counting sort, O(N+F)
   // (reference: O(N*F) double loop, CUDABasedRasterization.cpp:125-154; same ascending face order;
@@ -170,6 +165,23 @@ extern "C" int gvv_create(const gvv_desc* d, gvv_handle* out) {
     gvv_destroy(h);
     return fail(GVV_ECUDA, "topology upload failed: %s", cudaGetErrorString(e));
   }
+  // GVV_OPTIONS="key=value,key=value": gvv_set_option knobs applied to every new handle (tuning / A-B runs
+  // through wrappers that create their handles internally); unknown keys are an error
+  if (const char* env = getenv("GVV_OPTIONS")) {
+    std::string spec(env);
+    size_t pos = 0;
+    while (pos < spec.size()) {
+      size_t end = spec.find(',', pos);
+      if (end == std::string::npos) end = spec.size();
+      const std::string kv = spec.substr(pos, end - pos);
+      const size_t eq = kv.find('=');
+      if (eq != std::string::npos && eq > 0) {
+        const int rc = gvv_set_option(h, kv.substr(0, eq).c_str(), atoi(kv.c_str() + eq + 1));
+        if (rc != GVV_OK) { gvv_destroy(h); return fail(rc, "GVV_OPTIONS: bad entry '%s'", kv.c_str()); }
+      }
+      pos = end + 1;
+    }
+  }
   *out = h;
   return GVV_OK;
 }
@@ -179,9 +191,6 @@ extern "C" int gvv_destroy(gvv_handle h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   free_scratch(h->s);
-  if (h->sideStream) cudaStreamDestroy(h->sideStream);
-  if (h->evFork) cudaEventDestroy(h->evFork);
-  if (h->evJoin) cudaEventDestroy(h->evJoin);
   if (h->timer.ev) { for (int i = 0; i < 2 * KernelTimer::kCap; ++i) cudaEventDestroy(h->timer.ev[i]); delete[] h->timer.ev; delete[] h->timer.slot; }
   cudaFree(h->faces4); cudaFree(h->texcoords); cudaFree(h->vfOffsets); cudaFree(h->vfList); cudaFree(h->texelTable);
   delete h;
@@ -211,6 +220,7 @@ extern "C" int gvv_set_option(gvv_handle h, const char* key, int32_t value) {
   if (!strcmp(key, "texture_bilinear")) { h->texBilinear = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "spread_empty")) { h->spreadEmpty = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "heavy_mode")) { if (value < 0 || value > 2) return fail(GVV_EINVAL, "heavy_mode must be 0 (never), 1 (adaptive) or 2 (always)"); h->heavyMode = value; return GVV_OK; }
+  if (!strcmp(key, "heavy_slots")) { if (value < 1 || value > 1024) return fail(GVV_EINVAL, "heavy_slots must be in [1,1024]"); h->heavySlots = value; return GVV_OK; }
   if (!strcmp(key, "heavy_thr")) { if (value < 0) return fail(GVV_EINVAL, "heavy_thr must be >= 0"); h->heavyThr = value; return GVV_OK; }
   if (!strcmp(key, "split_unit")) { if (value < 0) return fail(GVV_EINVAL, "split_unit must be >= 0"); h->splitUnit = value; return GVV_OK; }
   if (!strcmp(key, "hiz")) { h->hiz = value ? 1 : 0; return GVV_OK; }
@@ -256,7 +266,7 @@ extern "C" int gvv_forward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
   FwdArgs a;
   a.B = B; a.C = h->C; a.N = h->N; a.F = h->F; a.W = h->W; a.H = h->H; a.texH = texH; a.texW = texW;
   a.albedo = h->albedo; a.shading = h->shading;
-  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin; a.rayCache = h->rayCache; a.batchDiv = h->batchDiv; a.ctaThreads = h->ctaThreads; a.interleave = h->interleave; a.hiz = h->hiz; a.spanZ = h->spanZ; a.splitUnit = h->splitUnit; a.heavyThr = h->heavyThr; a.heavyMode = h->heavyMode; a.ctaSlots = h->ctaSlots; a.spreadEmpty = h->spreadEmpty; a.texBilinear = h->texBilinear; a.sideStream = h->sideStream; a.evFork = h->evFork; a.evJoin = h->evJoin;
+  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin; a.rayCache = h->rayCache; a.batchDiv = h->batchDiv; a.ctaThreads = h->ctaThreads; a.interleave = h->interleave; a.hiz = h->hiz; a.spanZ = h->spanZ; a.splitUnit = h->splitUnit; a.heavyThr = h->heavyThr; a.heavySlots = h->heavySlots; a.heavyMode = h->heavyMode; a.ctaSlots = h->ctaSlots; a.spreadEmpty = h->spreadEmpty; a.texBilinear = h->texBilinear;
   a.vertex_pos = vertex_pos; a.vertex_color = vertex_color; a.texture = texture; a.sh_coeff = sh_coeff;
   a.extrinsics = extrinsics; a.intrinsics = intrinsics; a.texcoords = h->texcoords;
   a.faces4 = h->faces4; a.vfOffsets = h->vfOffsets; a.vfList = h->vfList;

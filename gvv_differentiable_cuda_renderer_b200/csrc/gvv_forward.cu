@@ -445,7 +445,7 @@ struct RasterParams {
   const float* texture; const float* texcoords; const float* sh_coeff;
   float* bary; int32_t* face; float* render;
   unsigned long long* ctaTrace;
-  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, spanZ, role, texBilinear;
+  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, spanZ, role, pdl, texBilinear;
   float cullMargin;
 };
 
@@ -532,6 +532,10 @@ raster_kernel(const RasterParams p) {
   // item = tile | strip << 20 | log2(K) << 24: this CTA owns rows [rowLo, rowLo + rowN) of the tile
   const int view = blockIdx.x % p.V;
   const int item = p.tileOrder[(size_t)view * p.nItems + blockIdx.x / p.V];
+  if (p.role == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // heavy launch: lets the 256-thread launch start beside it
+  // The 256-thread launch may FINISH before the heavy one; whatever follows in the stream only waits for this
+  // launch, so its last CTA (scheduled last) does not leave before the heavy launch has completed and flushed.
+  if (p.role == 0 && p.pdl && blockIdx.x == gridDim.x - 1) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (item < 0) return;                                // spare slot of the work list
   if (((item >> 28) & 1) != p.role) return;            // heavy items belong to the 1024-thread launch (role 1), the rest to role 0
   const int tile = item & 0xfffff;
@@ -1001,10 +1005,18 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   tm->begin(K_BIN_SCAN, st);
   const int nItems = a.nT + a.nT / 2;                  // Scratch::tileOrder is sized for this (gvv_api.cu)
   // Heavy bins (>= heavyThr triangles among the kHeavySlots heaviest items of a view) get a 1024-thread CTA, i.e.
-  // a whole SM, from a second launch on a side stream: a 256-thread CTA shares its SM with three others and
-  // would make the tile the critical path of the launch (measured: 236 us of a 274 us launch).
-  const int kHeavySlots = nItems < 32 ? nItems : 32;
-  const bool useHeavy = a.heavyMode > 0 && a.heavyThr > 0 && a.tile == 32 && !a.rayCache && a.ctaThreads == 256 && a.sideStream != nullptr;
+  // a whole SM, from a second launch: a 256-thread CTA shares its SM with three others and would make the
+  // tile the critical path of the launch (1M triangles at 3840x2160, one view: 1.53 ms -> 0.59 ms).  Which bins
+  // qualify is decided on the GPU (bin_scan_kernel).  A CTA that needs a whole SM must find one empty, and a
+  // launch of one such CTA per SM -- even one whose CTAs all leave at once -- slowed the end-to-end step through
+  // the Python layer by 10 % (a quarter of the SMs: nothing, measured).  So the heavy launch holds at most SMs/4
+  // CTAs, split evenly over the views, and is dropped when that leaves fewer than 16 per view (more than two views
+  // on a B200): a single tile can only be the critical path of a launch that has very few views -- the work of
+  // the other tiles grows with the number of views, the longest tile does not.  heavy_mode 2 skips this gate.
+  const int smCount = max(1, a.ctaSlots / 4);
+  const int kHeavySlots = min(min(nItems, a.heavySlots), max(1, (smCount / 4) / max(V, 1)));
+  const bool fewViews = (smCount / 4) / max(V, 1) >= 16 || a.heavyMode == 2;
+  const bool useHeavy = a.heavyMode > 0 && a.heavyThr > 0 && a.tile == 32 && !a.rayCache && a.ctaThreads == 256 && fewViews;
   const int maxLog = a.splitUnit > 0 ? (a.tile == 32 ? 3 : 2) : 0;
   bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.nT, nItems, a.splitUnit > 0 ? a.splitUnit : 1, maxLog,
                                       useHeavy ? a.heavyThr : 0, kHeavySlots, a.heavyMode == 2 ? -1 : max(1, a.ctaSlots / V), a.spreadEmpty, a.extrinsics, a.intrinsics, a.s.cams);
@@ -1038,32 +1050,40 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
 #undef GVV_RASTER_ATTR
     attrSet = true;
   }
-  // fork: the heavy launch goes FIRST and on the caller's stream, so that its one-SM CTAs are placed while the
-  // SMs are empty; the 256-thread launch follows on the side stream (a CTA that needs a whole SM would
-  // otherwise starve behind the small ones until the very end of the launch -- measured)
-  cudaStream_t ls = st;
+  // The heavy launch goes FIRST, so that its one-SM CTAs are placed while the SMs are empty (behind the small CTAs
+  // they would starve until the very end -- measured).  The 256-thread launch follows on the SAME stream as a
+  // programmatic dependent launch: the heavy CTAs signal griddepcontrol.launch_dependents as their first
+  // instruction, so the small CTAs start as soon as every heavy CTA is resident (or gone) and fill the other SMs.
+  // The two launches write disjoint tiles and both only read what bin_fill_kernel finished before the heavy
+  // launch began, so the dependent launch needs no griddepcontrol.wait.  (A side stream + events did the same but
+  // cost 12 % of the end-to-end step through the Python layer; this costs ~1 % when no bin is heavy.)
   if (useHeavy) {
     RasterParams ph = p;
-    ph.role = 1;
-    cudaEventRecord(a.evFork, st);
+    ph.role = 1; ph.pdl = 0;
     raster_kernel<32, false, 1024><<<dim3((unsigned)kHeavySlots * (unsigned)V), 1024, raster_smem_bytes<32, false, 1024>(), st>>>(ph);
-    cudaStreamWaitEvent(a.sideStream, a.evFork, 0);
-    ls = a.sideStream;
     ++launches;
   }
-  p.role = 0;
-#define GVV_RASTER_LAUNCH(TS, RC, NTH) raster_kernel<TS, RC, NTH><<<gridT, NTH, raster_smem_bytes<TS, RC, NTH>(), ls>>>(p)
-  if (a.tile == 16) {
-    if (a.rayCache) GVV_RASTER_LAUNCH(16, true, 256);
-    else if (a.ctaThreads == 128) GVV_RASTER_LAUNCH(16, false, 128);
-    else GVV_RASTER_LAUNCH(16, false, 256);
-  } else {
-    if (a.rayCache) GVV_RASTER_LAUNCH(32, true, 256);
-    else if (a.ctaThreads == 128) GVV_RASTER_LAUNCH(32, false, 128);
-    else GVV_RASTER_LAUNCH(32, false, 256);
-  }
+  p.role = 0; p.pdl = useHeavy ? 1 : 0;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = gridT; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = useHeavy ? 1 : 0;
+#define GVV_RASTER_LAUNCH(TS, RC, NTH) do { cfg.blockDim = dim3(NTH); cfg.dynamicSmemBytes = raster_smem_bytes<TS, RC, NTH>(); \
+                                            cudaLaunchKernelEx(&cfg, raster_kernel<TS, RC, NTH>, p); } while (0)
+    if (a.tile == 16) {
+      if (a.rayCache) GVV_RASTER_LAUNCH(16, true, 256);
+      else if (a.ctaThreads == 128) GVV_RASTER_LAUNCH(16, false, 128);
+      else GVV_RASTER_LAUNCH(16, false, 256);
+    } else {
+      if (a.rayCache) GVV_RASTER_LAUNCH(32, true, 256);
+      else if (a.ctaThreads == 128) GVV_RASTER_LAUNCH(32, false, 128);
+      else GVV_RASTER_LAUNCH(32, false, 256);
+    }
 #undef GVV_RASTER_LAUNCH
-  if (useHeavy) { cudaEventRecord(a.evJoin, a.sideStream); cudaStreamWaitEvent(st, a.evJoin, 0); }   // join
+  }
   tm->end(st);
   ++launches;
   return launch_ok() ? launches : -1;

@@ -65,8 +65,8 @@ struct gvv_renderer {
   int spreadEmpty = 0;        // raster: interleave the (HBM-bound) empty tiles with the (ALU-bound) non-empty ones
   int heavyMode = 1;          // 0 = never, 1 = only where such a bin would be the critical path of the launch (decided on the GPU), 2 = always
   int ctaSlots = 592;         // resident 256-thread raster CTAs of the device (4 per SM), set at create
-  int heavyThr = 768;         // raster: bins of >= heavyThr triangles are rasterised by 1024-thread CTAs on a side stream; 0 = off
-  cudaStream_t sideStream = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  int heavySlots = 32;        // raster: heavy candidates per view = the first heavySlots items of its work list
+  int heavyThr = 768;         // raster: bins of >= heavyThr triangles are candidates for the 1024-thread launch (one SM per tile)
   int splitUnit = 0;          // raster: a bin of >= splitUnit (2x, 4x) triangles is cut into 2 (4, 8) strips with a CTA each; 0 = never (measured slower: every strip re-scans the bin)
   int ctaTrace = 0;           // debug: record per-CTA start/end times of the raster kernel
   int spanZ = 2;              // raster: trim every row span to the pixels whose current winner the triangle could still beat (1 = both passes, 2 = far pass only)
@@ -92,8 +92,7 @@ namespace gvv {
 
 struct FwdArgs {
   int B, C, N, F, W, H, texH, texW, albedo, shading;
-  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, spanZ, splitUnit, heavyThr, heavyMode, ctaSlots, spreadEmpty, texBilinear;
-  cudaStream_t sideStream; cudaEvent_t evFork, evJoin;
+  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, spanZ, splitUnit, heavyThr, heavyMode, heavySlots, ctaSlots, spreadEmpty, texBilinear;
   float cullMargin;
   const float *vertex_pos, *vertex_color, *texture, *sh_coeff, *extrinsics, *intrinsics;
   const float* texcoords;
