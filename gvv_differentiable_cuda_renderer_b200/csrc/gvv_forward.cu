@@ -190,7 +190,8 @@ bin_count_kernel(const int4* __restrict__ faces4, const float4* __restrict__ pro
 }
 
 // exclusive scan of one view's tile histogram (one block per view) + the raster work list of the view.
-// A work item is a horizontal STRIP of a tile: item = tile | strip << 20 | log2(K) << 24, the tile being cut
+// A work item is a horizontal STRIP of a tile: item = tx | ty << 12 | strip << 24 | log2(K) << 27 | heavy << 29
+// (tile coordinates, so that the raster CTA needs no integer division), the tile being cut
 // into K = 1, 2, 4 or 8 strips of TS/K rows, each rasterised by its own CTA (every strip scans the whole
 // bin of the tile and keeps the rows that fall into it).  Heavy bins are split so that the longest CTA
 // of the launch -- the critical path: a pole/silhouette tile holds ~15x the average bin -- shrinks; the
@@ -203,7 +204,7 @@ __device__ __forceinline__ int strip_log2(int cnt, int unit, int maxLog) {
 }
 
 __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ tileCount, int* __restrict__ tileOffset,
-                                                        int* __restrict__ tileOrder, int nT, int nItems, int splitUnit, int maxLog,
+                                                        int* __restrict__ tileOrder, int nT, int tilesX, int nItems, int splitUnit, int maxLog,
                                                         int heavyThr, int heavySlots, int heavyLoad, int spreadEmpty,
                                                         const float* __restrict__ extr, const float* __restrict__ intr,
                                                         CamRec* __restrict__ cams) {
@@ -282,12 +283,12 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
         if (k > 0) pos += (int)(((long long)pos * n0) / n1);
         else { const int j = pos - n1; pos = j + min(n1, (int)((((long long)(j + 1)) * n1 + n0 - 1) / n0)); }
       }
-      // bit 28: the item is rasterised by the 1024-thread launch (one whole SM per tile) instead of a 256-thread CTA
+      // bit 29: the item is rasterised by the 1024-thread launch (one whole SM per tile) instead of a 256-thread CTA
       // ... when it would otherwise be the critical path of the launch: its bin is more than 1.4x the average
       // load of a 256-thread CTA slot (heavyLoad = slots / views, carry = bin entries of this view; heavyLoad < 0: always)
       const bool critical = heavyLoad < 0 || 5ll * w * heavyLoad > 7ll * carry;
-      const int heavy = (heavyThr > 0 && w >= heavyThr && pos < heavySlots && critical) ? (1 << 28) : 0;
-      order[pos] = i | (sidx << 20) | (l << 24) | heavy;
+      const int heavy = (heavyThr > 0 && w >= heavyThr && pos < heavySlots && critical) ? (1 << 29) : 0;
+      order[pos] = (i % tilesX) | ((i / tilesX) << 12) | (sidx << 24) | (l << 27) | heavy;
     }
   }
   for (int i = extraItems + threadIdx.x; i < nItems; i += blockDim.x) order[i] = -1;
@@ -445,7 +446,7 @@ struct RasterParams {
   const float* texture; const float* texcoords; const float* sh_coeff;
   float* bary; int32_t* face; float* render;
   unsigned long long* ctaTrace;
-  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, spanZ, role, pdl, texBilinear;
+  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, spanZ, role, pdl, grid2d, texBilinear;
   float cullMargin;
 };
 
@@ -528,22 +529,24 @@ raster_kernel(const RasterParams p) {
   __shared__ int sMinK, sMaxK, sLate;
   __shared__ unsigned sZmax;
 
-  // 1-D grid, view fastest: the heaviest work items of every view are scheduled first.
-  // item = tile | strip << 20 | log2(K) << 24: this CTA owns rows [rowLo, rowLo + rowN) of the tile
-  const int view = blockIdx.x % p.V;
-  const int item = p.tileOrder[(size_t)view * p.nItems + blockIdx.x / p.V];
+  // Grid (V, items): x = view runs fastest, so the heaviest work items of every view are scheduled first
+  // (1-D fallback with a division when the work list is longer than gridDim.y allows).
+  // item = tx | ty << 12 | strip << 24 | log2(K) << 27 | heavy << 29: this CTA owns rows [rowLo, rowLo + rowN) of tile (tx, ty)
+  const int view = p.grid2d ? (int)blockIdx.x : (int)(blockIdx.x % p.V);
+  const int rank = p.grid2d ? (int)blockIdx.y : (int)(blockIdx.x / p.V);
+  const int item = p.tileOrder[(size_t)view * p.nItems + rank];
   if (p.role == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // heavy launch: lets the 256-thread launch start beside it
   // The 256-thread launch may FINISH before the heavy one; whatever follows in the stream only waits for this
   // launch, so its last CTA (scheduled last) does not leave before the heavy launch has completed and flushed.
-  if (p.role == 0 && p.pdl && blockIdx.x == gridDim.x - 1) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (p.role == 0 && p.pdl && blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (item < 0) return;                                // spare slot of the work list
-  if (((item >> 28) & 1) != p.role) return;            // heavy items belong to the 1024-thread launch (role 1), the rest to role 0
-  const int tile = item & 0xfffff;
-  const int stripLog = (item >> 24) & 15, rowN = TS >> stripLog, rowLo = ((item >> 20) & 15) * rowN;
+  if (((item >> 29) & 1) != p.role) return;            // heavy items belong to the 1024-thread launch (role 1), the rest to role 0
+  const int tileX = item & 0xfff, tileY = (item >> 12) & 0xfff, tile = tileY * p.tilesX + tileX;
+  const int stripLog = (item >> 27) & 3, rowN = TS >> stripLog, rowLo = ((item >> 24) & 7) * rowN;
   const int qLo = rowLo * TS, qHi = (rowLo + rowN) * TS;
   const int b = view / p.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tileX0 = (tile % p.tilesX) * TS, tileY0 = (tile / p.tilesX) * TS;
+  const int tileX0 = tileX * TS, tileY0 = tileY * TS;
   const size_t tidx = (size_t)view * p.nT + tile;
   const int cntSmall = p.tileCount[tidx];
   const int cntBig = p.bigCount[view];
@@ -552,8 +555,9 @@ raster_kernel(const RasterParams p) {
     unsigned long long t; unsigned smid;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    p.ctaTrace[4 * (size_t)blockIdx.x] = t; p.ctaTrace[4 * (size_t)blockIdx.x + 1] = t;
-    p.ctaTrace[4 * (size_t)blockIdx.x + 2] = (unsigned long long)(cntSmall + cntBig); p.ctaTrace[4 * (size_t)blockIdx.x + 3] = smid;
+    const size_t lin = (size_t)rank * p.V + view;
+    p.ctaTrace[4 * lin] = t; p.ctaTrace[4 * lin + 1] = t;
+    p.ctaTrace[4 * lin + 2] = (unsigned long long)(cntSmall + cntBig); p.ctaTrace[4 * lin + 3] = smid;
   }
 
   if (cntSmall == 0 && cntBig == 0) {
@@ -932,7 +936,7 @@ raster_kernel(const RasterParams p) {
   }
   if (p.ctaTrace) {
     __syncthreads();
-    if (tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.ctaTrace[4 * (size_t)blockIdx.x + 1] = t; }
+    if (tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.ctaTrace[4 * ((size_t)rank * p.V + view) + 1] = t; }
   }
 }
 
@@ -1003,7 +1007,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   tm->end(st);
   ++launches;
   tm->begin(K_BIN_SCAN, st);
-  const int nItems = a.nT + a.nT / 2;                  // Scratch::tileOrder is sized for this (gvv_api.cu)
+  const int nItems = a.splitUnit > 0 ? a.nT + a.nT / 2 : a.nT;   // work-list slots per view (strips need spare ones); Scratch::tileOrder holds nT + nT/2
   // Heavy bins (>= heavyThr triangles among the kHeavySlots heaviest items of a view) get a 1024-thread CTA, i.e.
   // a whole SM, from a second launch: a 256-thread CTA shares its SM with three others and would make the
   // tile the critical path of the launch (1M triangles at 3840x2160, one view: 1.53 ms -> 0.59 ms).  Which bins
@@ -1018,7 +1022,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const bool fewViews = (smCount / 4) / max(V, 1) >= 16 || a.heavyMode == 2;
   const bool useHeavy = a.heavyMode > 0 && a.heavyThr > 0 && a.tile == 32 && !a.rayCache && a.ctaThreads == 256 && fewViews;
   const int maxLog = a.splitUnit > 0 ? (a.tile == 32 ? 3 : 2) : 0;
-  bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.nT, nItems, a.splitUnit > 0 ? a.splitUnit : 1, maxLog,
+  bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.nT, a.tilesX, nItems, a.splitUnit > 0 ? a.splitUnit : 1, maxLog,
                                       useHeavy ? a.heavyThr : 0, kHeavySlots, a.heavyMode == 2 ? -1 : max(1, a.ctaSlots / V), a.spreadEmpty, a.extrinsics, a.intrinsics, a.s.cams);
   tm->end(st);
   ++launches;
@@ -1040,7 +1044,8 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   p.bary = a.bary; p.face = a.face; p.render = a.render; p.ctaTrace = a.s.ctaTrace;
   p.C = a.C; p.N = a.N; p.F = a.F; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
   p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv; p.interleave = a.interleave; p.hiz = a.hiz; p.spanZ = a.spanZ; p.texBilinear = a.texBilinear;
-  const dim3 gridT((unsigned)nItems * (unsigned)V);
+  p.grid2d = nItems <= 65535 ? 1 : 0;
+  const dim3 gridT = p.grid2d ? dim3((unsigned)V, (unsigned)nItems) : dim3((unsigned)nItems * (unsigned)V);
   tm->begin(K_RASTER, st);
   static bool attrSet = false;
   if (!attrSet) {   // > 48 KB of dynamic shared memory needs the opt-in (once per process and device function)
@@ -1060,7 +1065,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   if (useHeavy) {
     RasterParams ph = p;
     ph.role = 1; ph.pdl = 0;
-    raster_kernel<32, false, 1024><<<dim3((unsigned)kHeavySlots * (unsigned)V), 1024, raster_smem_bytes<32, false, 1024>(), st>>>(ph);
+    raster_kernel<32, false, 1024><<<(p.grid2d ? dim3((unsigned)V, (unsigned)kHeavySlots) : dim3((unsigned)kHeavySlots * (unsigned)V)), 1024, raster_smem_bytes<32, false, 1024>(), st>>>(ph);
     ++launches;
   }
   p.role = 0; p.pdl = useHeavy ? 1 : 0;
