@@ -41,7 +41,7 @@ static cudaError_t dmalloc(T** p, size_t count) {
 
 static void free_scratch(Scratch& s) {
   cudaFree(s.cams); cudaFree(s.proj); cudaFree(s.vscaled); cudaFree(s.fnorm4); cudaFree(s.vnorm4); cudaFree(s.vcol4);
-  cudaFree(s.tileCount); cudaFree(s.tileCursor); cudaFree(s.tileOffset); cudaFree(s.tileOrder); cudaFree(s.tileDone); cudaFree(s.bigCount);
+  cudaFree(s.tileCount); cudaFree(s.tileCursor); cudaFree(s.tileCursorFar); cudaFree(s.tileMinK); cudaFree(s.tileMaxK); cudaFree(s.tileThr); cudaFree(s.tileOffset); cudaFree(s.tileOrder); cudaFree(s.tileDone); cudaFree(s.bigCount);
   cudaFree(s.bigList); cudaFree(s.bins); cudaFree(s.gnorm); cudaFree(s.bpos4); cudaFree(s.bcol4); cudaFree(s.bnor4); cudaFree(s.ctaTrace);
   s = Scratch();
 }
@@ -71,6 +71,10 @@ static int ensure_scratch(gvv_renderer* h, int B, cudaStream_t st) {
   acc(dmalloc(&s.vcol4, (size_t)B * N));
   acc(dmalloc(&s.tileCount, (size_t)V * nT));
   acc(dmalloc(&s.tileCursor, (size_t)V * nT));
+  acc(dmalloc(&s.tileCursorFar, (size_t)V * nT));
+  acc(dmalloc(&s.tileMinK, (size_t)V * nT));
+  acc(dmalloc(&s.tileMaxK, (size_t)V * nT));
+  acc(dmalloc(&s.tileThr, (size_t)V * nT));
   acc(dmalloc(&s.tileOffset, (size_t)V * nT));
   acc(dmalloc(&s.tileOrder, (size_t)V * (nT + nT / 2)));
   acc(dmalloc(&s.tileDone, (size_t)V * nT));
@@ -88,6 +92,9 @@ static int ensure_scratch(gvv_renderer* h, int B, cudaStream_t st) {
   }
   CK(cudaMemsetAsync(s.tileCount, 0, (size_t)V * nT * sizeof(int), st));
   CK(cudaMemsetAsync(s.tileCursor, 0, (size_t)V * nT * sizeof(int), st));
+  CK(cudaMemsetAsync(s.tileCursorFar, 0, (size_t)V * nT * sizeof(int), st));
+  CK(cudaMemsetAsync(s.tileMinK, 0x7f, (size_t)V * nT * sizeof(int), st));   // any value >= every key: bin_scan_kernel resets to INT_MAX
+  CK(cudaMemsetAsync(s.tileMaxK, 0x80, (size_t)V * nT * sizeof(int), st));   // 0x80808080 < every key
   CK(cudaMemsetAsync(s.tileDone, 0, (size_t)V * nT * sizeof(int), st));
   CK(cudaMemsetAsync(s.bigCount, 0, (size_t)V * sizeof(int), st));
   s.capViews = V;

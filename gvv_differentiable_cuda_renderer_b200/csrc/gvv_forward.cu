@@ -134,14 +134,24 @@ vertex_kernel(const float* __restrict__ vertex_pos, const float* __restrict__ ve
 // ------------------------------------------------------------------------------------------------
 // binning
 // ------------------------------------------------------------------------------------------------
-struct TileRange { int tx0, ty0, tx1, ty1, n; };
+// Lower bound of every depth key a triangle can produce: z = 1/(a/z0+b/z1+c/z2) with a,b,c in
+// [-0.001,1.001] stays above zmin*(1 - 0.003*zmax/zmin) >= 0.99*zmin when zmax <= 2 zmin; INT_MIN
+// (= no bound) otherwise.  Used only to SKIP work that provably cannot win the depth test.
+__device__ __forceinline__ int key_lower_bound(float z0, float z1, float z2) {
+  const float zmin = fminf(z0, fminf(z1, z2)), zmax = fmaxf(z0, fmaxf(z1, z2));
+  return (zmin > 0.f && zmax <= 2.f * zmin) ? __float2int_rd(zmin * 9900.f) - 1 : (int)0x80000000;
+}
+
+struct TileRange { int tx0, ty0, tx1, ty1, n, klb; };
 
 __device__ __forceinline__ TileRange tile_range(const int4* __restrict__ faces4, const float4* __restrict__ projv,
                                                 int f, int W, int H, int tileShift) {
   const int4 fc = __ldg(faces4 + f);
-  const int4 bb = bbox_exact(__ldg(projv + fc.x), __ldg(projv + fc.y), __ldg(projv + fc.z), W, H);
+  const float4 p0 = __ldg(projv + fc.x), p1 = __ldg(projv + fc.y), p2 = __ldg(projv + fc.z);
+  const int4 bb = bbox_exact(p0, p1, p2, W, H);
   TileRange r;
   r.n = 0;
+  r.klb = key_lower_bound(p0.z, p1.z, p2.z);
   if (bb.x > bb.z || bb.y > bb.w) { r.tx0 = r.ty0 = 0; r.tx1 = r.ty1 = -1; return r; }
   r.tx0 = bb.x >> tileShift; r.tx1 = bb.z >> tileShift;
   r.ty0 = bb.y >> tileShift; r.ty1 = bb.w >> tileShift;
@@ -153,15 +163,24 @@ __device__ __forceinline__ TileRange tile_range(const int4* __restrict__ faces4,
 // flushing the per-block tile histogram (nT entries) is amortised over 1024 triangles.
 constexpr int kBinFacesPerThread = 4;
 
+// The binning also prepares the two depth passes of the raster kernel ("hierarchical z"): per tile the range
+// [min, max] of the depth-key lower bounds of its triangles (bin_count_kernel), the threshold in the middle of
+// it (bin_scan_kernel), and bins filled with the NEAR triangles (lower bound <= threshold) from the front and
+// the FAR ones from the back (bin_fill_kernel), so that the raster warps set every triangle up exactly once.
+constexpr int kNoBound = (int)0x80000000;   // key_lower_bound of a triangle without a usable bound: always "near"
+
 template <bool SMEM_HIST>
 __global__ void __launch_bounds__(256)
 bin_count_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj, int* __restrict__ tileCount,
+                 int* __restrict__ tileMinK, int* __restrict__ tileMaxK,
                  int* __restrict__ bigCount, int* __restrict__ bigList, int F, int N, int W, int H, int tileShift,
                  int tilesX, int nT) {
-  extern __shared__ int hist[];
+  extern __shared__ int hist[];   // SMEM_HIST: hist[nT], mn[nT], mx[nT]
+  int* mn = hist + nT;
+  int* mx = hist + 2 * nT;
   const int view = blockIdx.y;
   if (SMEM_HIST) {
-    for (int i = threadIdx.x; i < nT; i += blockDim.x) hist[i] = 0;
+    for (int i = threadIdx.x; i < nT; i += blockDim.x) { hist[i] = 0; mn[i] = 0x7fffffff; mx[i] = kNoBound; }
     __syncthreads();
   }
 #pragma unroll
@@ -175,8 +194,14 @@ bin_count_kernel(const int4* __restrict__ faces4, const float4* __restrict__ pro
     } else if (r.n > 0) {
       for (int ty = r.ty0; ty <= r.ty1; ++ty)
         for (int tx = r.tx0; tx <= r.tx1; ++tx) {
-          if (SMEM_HIST) atomicAdd(&hist[ty * tilesX + tx], 1);
-          else atomicAdd(tileCount + (size_t)view * nT + ty * tilesX + tx, 1);
+          const int t = ty * tilesX + tx;
+          if (SMEM_HIST) {
+            atomicAdd(&hist[t], 1);
+            if (r.klb != kNoBound) { atomicMin(&mn[t], r.klb); atomicMax(&mx[t], r.klb); }
+          } else {
+            atomicAdd(tileCount + (size_t)view * nT + t, 1);
+            if (r.klb != kNoBound) { atomicMin(tileMinK + (size_t)view * nT + t, r.klb); atomicMax(tileMaxK + (size_t)view * nT + t, r.klb); }
+          }
         }
     }
   }
@@ -184,7 +209,10 @@ bin_count_kernel(const int4* __restrict__ faces4, const float4* __restrict__ pro
     __syncthreads();
     for (int i = threadIdx.x; i < nT; i += blockDim.x) {
       const int c = hist[i];
-      if (c) atomicAdd(tileCount + (size_t)view * nT + i, c);
+      if (c) {
+        atomicAdd(tileCount + (size_t)view * nT + i, c);
+        if (mx[i] != kNoBound) { atomicMin(tileMinK + (size_t)view * nT + i, mn[i]); atomicMax(tileMaxK + (size_t)view * nT + i, mx[i]); }
+      }
     }
   }
 }
@@ -204,7 +232,8 @@ __device__ __forceinline__ int strip_log2(int cnt, int unit, int maxLog) {
 }
 
 __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ tileCount, int* __restrict__ tileOffset,
-                                                        int* __restrict__ tileOrder, int nT, int tilesX, int nItems, int splitUnit, int maxLog,
+                                                        int* __restrict__ tileOrder, int* __restrict__ tileMinK, int* __restrict__ tileMaxK, int* __restrict__ tileThr,
+                                                        int nT, int tilesX, int nItems, int splitUnit, int maxLog,
                                                         int heavyThr, int heavySlots, int heavyLoad, int spreadEmpty,
                                                         const float* __restrict__ extr, const float* __restrict__ intr,
                                                         CamRec* __restrict__ cams) {
@@ -236,6 +265,14 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
     __syncthreads();
     if (threadIdx.x == 0) carry += warpSum[31];
     __syncthreads();
+  }
+  // near/far threshold of every tile = middle of the range of its depth-key lower bounds; the range is reset
+  // for the next call (self-cleaning scratch)
+  for (int i = threadIdx.x; i < nT; i += blockDim.x) {
+    const size_t ti = (size_t)view * nT + i;
+    const int lo = tileMinK[ti], hi = tileMaxK[ti];
+    tileThr[ti] = hi > lo ? lo + ((hi - lo) >> 1) : 0x7fffffff;
+    tileMinK[ti] = 0x7fffffff; tileMaxK[ti] = kNoBound;
   }
   // strips per tile: double the split unit until the extra items fit into the nItems - nT spare slots
   int unit = splitUnit;
@@ -300,37 +337,50 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
 template <bool SMEM_HIST>
 __global__ void __launch_bounds__(256)
 bin_fill_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj, const int* __restrict__ tileOffset,
-                int* __restrict__ tileCursor, int* __restrict__ bins, int F, int N, int W, int H, int tileShift,
+                const int* __restrict__ tileCount, const int* __restrict__ tileThr,
+                int* __restrict__ tileCursor, int* __restrict__ tileCursorFar, int* __restrict__ bins, int F, int N, int W, int H, int tileShift,
                 int tilesX, int nT) {
-  extern __shared__ int sm[];   // SMEM_HIST: hist[nT] then base[nT]
-  int* hist = sm;
-  int* base = sm + nT;
+  extern __shared__ int sm[];   // SMEM_HIST: histN[nT], histF[nT], baseN[nT], baseF[nT]
+  int* histN = sm;
+  int* histF = sm + nT;
+  int* baseN = sm + 2 * nT;
+  int* baseF = sm + 3 * nT;
   const int view = blockIdx.y;
   TileRange r[kBinFacesPerThread];
   int fid[kBinFacesPerThread];
 #pragma unroll
   for (int k = 0; k < kBinFacesPerThread; ++k) {
     fid[k] = (blockIdx.x * kBinFacesPerThread + k) * blockDim.x + threadIdx.x;
-    r[k].n = 0; r[k].tx0 = r[k].ty0 = 0; r[k].tx1 = r[k].ty1 = -1;
+    r[k].n = 0; r[k].tx0 = r[k].ty0 = 0; r[k].tx1 = r[k].ty1 = -1; r[k].klb = kNoBound;
     if (fid[k] < F) r[k] = tile_range(faces4, proj + (size_t)view * N, fid[k], W, H, tileShift);
     if (r[k].n > kMaxSmallTiles) r[k].n = 0;      // big triangles live in the big list (bin_count_kernel)
   }
   int* viewBins = bins + (size_t)view * F * kMaxSmallTiles;
   const int* off = tileOffset + (size_t)view * nT;
-  int* cur = tileCursor + (size_t)view * nT;
+  const int* cnt = tileCount + (size_t)view * nT;
+  const int* thr = tileThr + (size_t)view * nT;
+  int* curN = tileCursor + (size_t)view * nT;
+  int* curF = tileCursorFar + (size_t)view * nT;
+  // a triangle is FAR in a tile when its depth-key lower bound is beyond the tile's threshold
+  auto is_far = [&](int klb, int t) { return klb != kNoBound && klb > __ldg(thr + t); };
   if (SMEM_HIST) {
-    for (int i = threadIdx.x; i < nT; i += blockDim.x) hist[i] = 0;
+    for (int i = threadIdx.x; i < 2 * nT; i += blockDim.x) sm[i] = 0;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kBinFacesPerThread; ++k)
       if (r[k].n > 0)
         for (int ty = r[k].ty0; ty <= r[k].ty1; ++ty)
-          for (int tx = r[k].tx0; tx <= r[k].tx1; ++tx) atomicAdd(&hist[ty * tilesX + tx], 1);
+          for (int tx = r[k].tx0; tx <= r[k].tx1; ++tx) {
+            const int t = ty * tilesX + tx;
+            atomicAdd(is_far(r[k].klb, t) ? &histF[t] : &histN[t], 1);
+          }
     __syncthreads();
-    // one global reservation per tile this block touches
+    // one global reservation per tile and side this block touches: near entries grow from the front of the
+    // tile's segment, far entries from its back
     for (int i = threadIdx.x; i < nT; i += blockDim.x) {
-      const int c = hist[i];
-      if (c) { base[i] = off[i] + atomicAdd(cur + i, c); hist[i] = 0; }
+      const int cN = histN[i], cF = histF[i];
+      if (cN) { baseN[i] = off[i] + atomicAdd(curN + i, cN); histN[i] = 0; }
+      if (cF) { baseF[i] = off[i] + cnt[i] - atomicAdd(curF + i, cF) - cF; histF[i] = 0; }
     }
     __syncthreads();
 #pragma unroll
@@ -339,7 +389,8 @@ bin_fill_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj
         for (int ty = r[k].ty0; ty <= r[k].ty1; ++ty)
           for (int tx = r[k].tx0; tx <= r[k].tx1; ++tx) {
             const int t = ty * tilesX + tx;
-            viewBins[base[t] + atomicAdd(&hist[t], 1)] = fid[k];
+            if (is_far(r[k].klb, t)) viewBins[baseF[t] + atomicAdd(&histF[t], 1)] = fid[k];
+            else viewBins[baseN[t] + atomicAdd(&histN[t], 1)] = fid[k];
           }
   } else {
 #pragma unroll
@@ -348,7 +399,8 @@ bin_fill_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj
         for (int ty = r[k].ty0; ty <= r[k].ty1; ++ty)
           for (int tx = r[k].tx0; tx <= r[k].tx1; ++tx) {
             const int t = ty * tilesX + tx;
-            viewBins[off[t] + atomicAdd(cur + t, 1)] = fid[k];
+            if (is_far(r[k].klb, t)) viewBins[off[t] + cnt[t] - 1 - atomicAdd(curF + t, 1)] = fid[k];
+            else viewBins[off[t] + atomicAdd(curN + t, 1)] = fid[k];
           }
   }
 }
@@ -442,7 +494,7 @@ __device__ __forceinline__ void edge_setup(float4 p0, float4 p1, float4 p2, floa
 struct RasterParams {
   const int4* faces4; const float4* proj; const float4* vscaled; const float4* vnorm4; const float4* vcol4;
   const CamRec* cams;
-  int* tileCount; int* tileCursor; int* tileDone; const int* tileOffset; const int* tileOrder; const int* bigCount; const int* bigList; const int* bins;
+  int* tileCount; int* tileCursor; int* tileCursorFar; int* tileDone; const int* tileOffset; const int* tileOrder; const int* bigCount; const int* bigList; const int* bins;
   const float* texture; const float* texcoords; const float* sh_coeff;
   float* bary; int32_t* face; float* render;
   unsigned long long* ctaTrace;
@@ -494,14 +546,6 @@ __device__ __forceinline__ ZEntry cas128_shared(ZEntry* addr, ZEntry cmp, ZEntry
   return old;
 }
 
-// Lower bound of every depth key a triangle can produce: z = 1/(a/z0+b/z1+c/z2) with a,b,c in
-// [-0.001,1.001] stays above zmin*(1 - 0.003*zmax/zmin) >= 0.99*zmin when zmax <= 2 zmin; INT_MIN
-// (= no bound) otherwise.  Used only to SKIP work that provably cannot win the depth test.
-__device__ __forceinline__ int key_lower_bound(float z0, float z1, float z2) {
-  const float zmin = fminf(z0, fminf(z1, z2)), zmax = fmaxf(z0, fmaxf(z1, z2));
-  return (zmin > 0.f && zmax <= 2.f * zmin) ? __float2int_rd(zmin * 9900.f) - 1 : (int)0x80000000;
-}
-
 // Shared-memory plan of raster_kernel (dynamic, carved by hand):
 //   zt[TS*TS] ZEntry | rayx,rayy,rayz[TS*TS] f32 (RC only) | per warp: rec[kBatch], erec[kBatch], startArr[60], qStart[96], qInfo[64]
 constexpr int kBatch = 24;   // triangles a warp sets up at a time
@@ -526,7 +570,6 @@ raster_kernel(const RasterParams p) {
   __shared__ float shc[27];
   __shared__ CamRec cam;
   __shared__ int nextBatch;
-  __shared__ int sMinK, sMaxK, sLate;
   __shared__ unsigned sZmax;
 
   // Grid (V, items): x = view runs fastest, so the heaviest work items of every view are scheduled first
@@ -597,7 +640,7 @@ raster_kernel(const RasterParams p) {
 
   if (tid < 64) reinterpret_cast<float*>(&cam)[tid] = reinterpret_cast<const float*>(p.cams + view)[tid];
   if (tid >= 64 && tid < 64 + 27) shc[tid - 64] = p.sh_coeff[(size_t)view * 27 + (tid - 64)];
-  if (tid == 96) { nextBatch = 0; sMinK = 0x7fffffff; sMaxK = (int)0x80000000; sLate = 0; sZmax = 0u; }
+  if (tid == 96) { nextBatch = 0; sZmax = 0u; }
   __syncthreads();
   const F3 ros = mk3(cam.ros[0], cam.ros[1], cam.ros[2]);
 
@@ -655,36 +698,24 @@ raster_kernel(const RasterParams p) {
   };
 
   const int cntAll = cntSmall + cntBig;
-  const int G = min(kBatch, max(1, (cntAll + p.batchDiv - 1) / p.batchDiv));   // triangles per batch: a short bin is spread over the warps
-  const int nBatches = (cntAll + G - 1) / G;
   const int* smallList = p.bins + (size_t)view * p.F * kMaxSmallTiles + p.tileOffset[tidx];
   const int* bigList = p.bigList + (size_t)view * p.F;
   const float4* vs = p.vscaled + (size_t)b * p.N;
   const float4* pj = p.proj + (size_t)view * p.N;
 
-  // ---- hierarchical z.  The bin is rasterised in two passes: first the triangles whose depth-key
-  // lower bound lies in the nearer half of the bin's range, then the rest -- and a triangle of the
-  // second pass whose lower bound is behind EVERY pixel of the (by then fully covered) z-tile is
-  // dropped before any of its rows is touched.  Keys only ever decrease, so such a triangle can win
-  // no pixel: the result is bit-identical (hiz = 0 rasterises everything in one pass). ----
-  int thr = 0x7fffffff;                               // pass 0 takes lower bounds <= thr
-  if (p.hiz && cntAll >= 64) {
-    int mn = 0x7fffffff, mx = (int)0x80000000;
-    for (int i = tid; i < cntAll; i += NTH) {
-      const int4 fc = __ldg(p.faces4 + __ldg(i < cntSmall ? smallList + i : bigList + (i - cntSmall)));
-      const int k = key_lower_bound(__ldg(pj + fc.x).z, __ldg(pj + fc.y).z, __ldg(pj + fc.z).z);
-      if (k != (int)0x80000000) { mn = min(mn, k); mx = max(mx, k); }
-    }
-    mn = __reduce_min_sync(FULL_MASK, mn); mx = __reduce_max_sync(FULL_MASK, mx);
-    if (lane == 0) { atomicMin(&sMinK, mn); atomicMax(&sMaxK, mx); }
-    __syncthreads();
-    if (sMaxK > sMinK) thr = sMinK + ((sMaxK - sMinK) >> 1);
-  }
+  // ---- hierarchical z.  The bin arrives partitioned (bin_fill_kernel): first the nNear triangles whose
+  // depth-key lower bound lies in the nearer half of the bin's range, then the far ones.  It is rasterised
+  // in two passes, near (+ the view's big triangles) then far, and a far triangle whose lower bound is behind
+  // EVERY pixel of the (by then fully covered) z-tile is dropped before any of its rows is touched.  Keys only
+  // ever decrease, so such a triangle can win no pixel: the result is bit-identical (hiz = 0 and short bins
+  // rasterise everything in one pass). ----
+  const int nNear = p.tileCursor[tidx];
+  const bool twoPass = p.hiz && cntAll >= 64 && nNear < cntSmall;
   for (int pass = 0; pass < 2; ++pass) {
   unsigned zmaxBits = 0xffffffffu;                    // pass 1: farthest current winner of the tile (0xffffffff if a pixel is still empty)
   if (pass == 1) {
+    if (!twoPass) break;
     __syncthreads();                                  // pass 0 complete
-    if (sLate == 0) break;                            // nothing was deferred
     unsigned m = 0u;
     for (int q = qLo + tid; q < qHi; q += NTH) {
       const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
@@ -696,20 +727,25 @@ raster_kernel(const RasterParams p) {
     __syncthreads();
     zmaxBits = sZmax;
   }
+  const int passLo = pass == 0 ? 0 : nNear;                                     // first bin entry of this pass
+  const int nSmall = pass == 0 ? (twoPass ? nNear : cntSmall) : cntSmall - nNear;   // bin entries of this pass
+  const int nPass = nSmall + (pass == 0 ? cntBig : 0);                           // + the big list in pass 0
+  const int G = min(kBatch, max(1, (nPass + p.batchDiv - 1) / p.batchDiv));   // triangles per batch: a short bin is spread over the warps
+  const int nBatches = (nPass + G - 1) / G;
   for (;;) {
-    // batch j takes the bin entries j, j + nBatches, j + 2 nBatches, ... (interleave = 1, the default):
+    // batch j takes the entries j, j + nBatches, j + 2 nBatches, ... (interleave = 1, the default):
     // every warp gets a sample of the whole bin instead of one spatially coherent chunk, which evens
-    // out the batches and shortens the wait at the barrier before the resolve stage
+    // out the batches and shortens the wait at the barriers
     int base = 0;
     if (lane == 0) base = atomicAdd(&nextBatch, p.interleave ? 1 : G);
     base = __shfl_sync(FULL_MASK, base, 0);
-    if (base >= (p.interleave ? nBatches : cntAll)) break;
+    if (base >= (p.interleave ? nBatches : nPass)) break;
     const int i = p.interleave ? base + lane * nBatches : base + lane;
     int n = 0;
     TriRec mine;
     EdgeRec em;
-    if (lane < G && i < cntAll) {
-      const int f = __ldg(i < cntSmall ? smallList + i : bigList + (i - cntSmall));
+    if (lane < G && i < nPass) {
+      const int f = __ldg(i < nSmall ? smallList + passLo + i : bigList + (i - nSmall));
       const int4 fc = __ldg(p.faces4 + f);
       const float4 s0 = __ldg(vs + fc.x), s1 = __ldg(vs + fc.y), s2 = __ldg(vs + fc.z);
       const float4 p0 = __ldg(pj + fc.x), p1 = __ldg(pj + fc.y), p2 = __ldg(pj + fc.z);
@@ -718,10 +754,8 @@ raster_kernel(const RasterParams p) {
       const int cy0 = max(bb.y, tileY0 + rowLo), cy1 = min(bb.w, tileY0 + rowLo + rowN - 1);
       const int w = cx1 - cx0 + 1, h = cy1 - cy0 + 1;
       const int klb = key_lower_bound(p0.z, p1.z, p2.z);
-      const bool late = klb > thr;                     // belongs to pass 1
-      bool take = (w > 0 && h > 0) && (late == (pass == 1));
-      if (pass == 0 && late && w > 0 && h > 0) sLate = 1;          // benign race: every writer stores 1
-      if (pass == 1 && take && (unsigned)(klb ^ 0x80000000) > zmaxBits) take = false;   // behind the whole tile
+      bool take = w > 0 && h > 0;
+      if (pass == 1 && (unsigned)(klb ^ 0x80000000) > zmaxBits) take = false;   // behind the whole tile
       if (take) {
         n = h;                 // work items are ROWS of the clipped bbox
         const TriSetup ts = tri_setup_exact(mk3(s0.x, s0.y, s0.z), mk3(s1.x, s1.y, s1.z), mk3(s2.x, s2.y, s2.z), ros);
@@ -932,7 +966,7 @@ raster_kernel(const RasterParams p) {
   // self-cleaning scratch: the last strip of the tile to finish resets the tile's counters (every strip
   // read them before it got here)
   if (tid == 0) {
-    if (stripLog == 0 || atomicAdd(p.tileDone + tidx, 1) == (1 << stripLog) - 1) { p.tileCount[tidx] = 0; p.tileCursor[tidx] = 0; p.tileDone[tidx] = 0; }
+    if (stripLog == 0 || atomicAdd(p.tileDone + tidx, 1) == (1 << stripLog) - 1) { p.tileCount[tidx] = 0; p.tileCursor[tidx] = 0; p.tileCursorFar[tidx] = 0; p.tileDone[tidx] = 0; }
   }
   if (p.ctaTrace) {
     __syncthreads();
@@ -998,11 +1032,11 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const dim3 gridF((a.F + 256 * kBinFacesPerThread - 1) / (256 * kBinFacesPerThread), V);
   tm->begin(K_BIN_COUNT, st);
   if (a.nT <= kSmemHistTiles) {
-    bin_count_kernel<true><<<gridF, 256, a.nT * sizeof(int), st>>>(a.faces4, a.s.proj, a.s.tileCount, a.s.bigCount, a.s.bigList,
-                                                                  a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
+    bin_count_kernel<true><<<gridF, 256, 3 * a.nT * sizeof(int), st>>>(a.faces4, a.s.proj, a.s.tileCount, a.s.tileMinK, a.s.tileMaxK,
+                                                                      a.s.bigCount, a.s.bigList, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
   } else {
-    bin_count_kernel<false><<<gridF, 256, 0, st>>>(a.faces4, a.s.proj, a.s.tileCount, a.s.bigCount, a.s.bigList,
-                                                  a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
+    bin_count_kernel<false><<<gridF, 256, 0, st>>>(a.faces4, a.s.proj, a.s.tileCount, a.s.tileMinK, a.s.tileMaxK,
+                                                  a.s.bigCount, a.s.bigList, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
   }
   tm->end(st);
   ++launches;
@@ -1022,23 +1056,27 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const bool fewViews = (smCount / 4) / max(V, 1) >= 16 || a.heavyMode == 2;
   const bool useHeavy = a.heavyMode > 0 && a.heavyThr > 0 && a.tile == 32 && !a.rayCache && a.ctaThreads == 256 && fewViews;
   const int maxLog = a.splitUnit > 0 ? (a.tile == 32 ? 3 : 2) : 0;
-  bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.nT, a.tilesX, nItems, a.splitUnit > 0 ? a.splitUnit : 1, maxLog,
+  bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.s.tileMinK, a.s.tileMaxK, a.s.tileThr, a.nT, a.tilesX, nItems, a.splitUnit > 0 ? a.splitUnit : 1, maxLog,
                                       useHeavy ? a.heavyThr : 0, kHeavySlots, a.heavyMode == 2 ? -1 : max(1, a.ctaSlots / V), a.spreadEmpty, a.extrinsics, a.intrinsics, a.s.cams);
   tm->end(st);
   ++launches;
   tm->begin(K_BIN_FILL, st);
   if (a.nT <= kSmemHistTiles) {
-    bin_fill_kernel<true><<<gridF, 256, 2 * a.nT * sizeof(int), st>>>(a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCursor, a.s.bins,
+    static bool fillAttr = false;
+    if (!fillAttr) { cudaFuncSetAttribute(bin_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSmemHistTiles * (int)sizeof(int)); fillAttr = true; }
+    bin_fill_kernel<true><<<gridF, 256, 4 * a.nT * sizeof(int), st>>>(a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCount, a.s.tileThr,
+                                                                     a.s.tileCursor, a.s.tileCursorFar, a.s.bins,
                                                                      a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
   } else {
-    bin_fill_kernel<false><<<gridF, 256, 0, st>>>(a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCursor, a.s.bins,
+    bin_fill_kernel<false><<<gridF, 256, 0, st>>>(a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCount, a.s.tileThr,
+                                                 a.s.tileCursor, a.s.tileCursorFar, a.s.bins,
                                                  a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
   }
   tm->end(st);
   ++launches;
   RasterParams p;
   p.faces4 = a.faces4; p.proj = a.s.proj; p.vscaled = a.s.vscaled; p.vnorm4 = a.s.vnorm4; p.vcol4 = a.s.vcol4;
-  p.cams = a.s.cams; p.tileCount = a.s.tileCount; p.tileCursor = a.s.tileCursor; p.tileDone = a.s.tileDone; p.nItems = nItems; p.tileOffset = a.s.tileOffset; p.tileOrder = a.s.tileOrder; p.V = V;
+  p.cams = a.s.cams; p.tileCount = a.s.tileCount; p.tileCursor = a.s.tileCursor; p.tileCursorFar = a.s.tileCursorFar; p.tileDone = a.s.tileDone; p.nItems = nItems; p.tileOffset = a.s.tileOffset; p.tileOrder = a.s.tileOrder; p.V = V;
   p.bigCount = a.s.bigCount; p.bigList = a.s.bigList; p.bins = a.s.bins;
   p.texture = a.texture; p.texcoords = a.texcoords; p.sh_coeff = a.sh_coeff;
   p.bary = a.bary; p.face = a.face; p.render = a.render; p.ctaTrace = a.s.ctaTrace;

@@ -22,7 +22,11 @@ struct Scratch {
   float4* vnorm4 = nullptr;      // [B*N]  unnormalised vertex normal
   float4* vcol4 = nullptr;       // [B*N]  vertex colour
   int* tileCount = nullptr;      // [V*nT] self-cleaning (the raster kernel zeroes its own entry)
-  int* tileCursor = nullptr;     // [V*nT] self-cleaning
+  int* tileCursor = nullptr;     // [V*nT] near triangles filled into the tile's bin (from its front); self-cleaning
+  int* tileCursorFar = nullptr;  // [V*nT] far triangles filled (from the back of the bin); self-cleaning
+  int* tileMinK = nullptr;       // [V*nT] min / max depth-key lower bound of the tile's triangles; reset by bin_scan_kernel
+  int* tileMaxK = nullptr;
+  int* tileThr = nullptr;        // [V*nT] near/far threshold of the tile
   int* tileOffset = nullptr;     // [V*nT]
   int* tileOrder = nullptr;      // [V*(nT+nT/2)] raster work items (tile strips) of a view, heaviest first; -1 = unused slot
   int* tileDone = nullptr;       // [V*nT] strips of a split tile that have finished; self-cleaning
