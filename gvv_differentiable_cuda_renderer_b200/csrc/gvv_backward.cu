@@ -102,6 +102,7 @@ struct PixelParams {
 };
 
 constexpr int kVals = 27;
+constexpr int kShRows = 12;  // rows 27..38 of the warp buffer: g*albedo (3) and the SH basis (9) of every pixel, for the SH gradient
 constexpr int kRow = 36;    // 32 pixels + 4 pad: a quarter-warp's float4 reads of 8 different rows hit 32 different banks
 
 // Tolerance-level arithmetic of the backward: reciprocal-multiply instead of IEEE divides
@@ -148,7 +149,7 @@ constexpr int kSlabs = 4;
 
 __global__ void __launch_bounds__(256, 4)
 pixel_grad_kernel(const PixelParams p) {
-  __shared__ __align__(16) float buf[8][kVals * kRow];   // per warp: value-major, kRow floats per value (32 pixels + pad)
+  __shared__ __align__(16) float buf[8][(kVals + kShRows) * kRow];   // per warp: value-major, kRow floats per value (32 pixels + pad)
   __shared__ float shPart[8][kVals];
   __shared__ CamRec cam;
   __shared__ float shc[27];
@@ -269,6 +270,11 @@ pixel_grad_kernel(const PixelParams p) {
         }
       }
       gA[0] = g.x * alb[0]; gA[1] = g.y * alb[1]; gA[2] = g.z * alb[2];
+      if (shaded) {   // parked in the warp buffer now, so that Y and gA do not stay live across the scatter stage
+        mine[(kVals + 0) * kRow] = gA[0]; mine[(kVals + 1) * kRow] = gA[1]; mine[(kVals + 2) * kRow] = gA[2];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) mine[(kVals + 3 + k) * kRow] = Y[k];
+      }
 
       float pos9[9];
 #pragma unroll
@@ -389,13 +395,14 @@ pixel_grad_kernel(const PixelParams p) {
   // ---- SH gradient: 12 values per pixel (g*albedo, Y) stored value-major; lane j = (ch,k) sums
   // gA[ch]*Y[k] over the 32 pixels with float4 reads (uncovered pixels store zeros) ----
   if (shaded) {
-    mine[0 * kRow] = gA[0]; mine[1 * kRow] = gA[1]; mine[2 * kRow] = gA[2];   // zeros where not covered
+    if (!covered) {   // zeros where not covered
 #pragma unroll
-    for (int k = 0; k < 9; ++k) mine[(3 + k) * kRow] = Y[k];
+      for (int k = 0; k < kShRows; ++k) mine[(kVals + k) * kRow] = 0.f;
+    }
     __syncwarp();
     if (lane < kVals) {
-      const float4* pa = reinterpret_cast<const float4*>(mybuf + (lane / 9) * kRow);
-      const float4* py = reinterpret_cast<const float4*>(mybuf + (3 + lane % 9) * kRow);
+      const float4* pa = reinterpret_cast<const float4*>(mybuf + (kVals + lane / 9) * kRow);
+      const float4* py = reinterpret_cast<const float4*>(mybuf + (kVals + 3 + lane % 9) * kRow);
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const float4 a4 = pa[g], y4 = py[g];
