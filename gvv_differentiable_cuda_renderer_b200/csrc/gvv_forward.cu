@@ -134,12 +134,15 @@ vertex_kernel(const float* __restrict__ vertex_pos, const float* __restrict__ ve
 // ------------------------------------------------------------------------------------------------
 // binning
 // ------------------------------------------------------------------------------------------------
-// Lower bound of every depth key a triangle can produce: z = 1/(a/z0+b/z1+c/z2) with a,b,c in
-// [-0.001,1.001] stays above zmin*(1 - 0.003*zmax/zmin) >= 0.99*zmin when zmax <= 2 zmin; INT_MIN
-// (= no bound) otherwise.  Used only to SKIP work that provably cannot win the depth test.
+// Lower bound of every depth key a triangle can produce.  z = 1/s, s = a/z0 + b/z1 + c/z2 with a,b,c in
+// [-0.001, 1.001] and a+b+c = 1: the largest s puts weight 1.001 on the smallest depth and -0.001 on another,
+// s <= 1.001/zmin, and with zmax <= 2 zmin the smallest s stays positive (>= (0.501 - 0.002)/zmin), so
+// z >= zmin/1.001 = 0.999001 zmin.  The bound uses 0.9985 zmin (fp32 rounding of the five operations of
+// depth_key_exact is ~1e-6 relative) and one key unit of slack; INT_MIN (= no bound) when the ratio test fails.
+// Used only to SKIP work that provably cannot win the depth test.
 __device__ __forceinline__ int key_lower_bound(float z0, float z1, float z2) {
   const float zmin = fminf(z0, fminf(z1, z2)), zmax = fmaxf(z0, fmaxf(z1, z2));
-  return (zmin > 0.f && zmax <= 2.f * zmin) ? __float2int_rd(zmin * 9900.f) - 1 : (int)0x80000000;
+  return (zmin > 0.f && zmax <= 2.f * zmin) ? __float2int_rd(zmin * 9985.f) - 1 : (int)0x80000000;
 }
 
 struct TileRange { int tx0, ty0, tx1, ty1, n, klb; };
@@ -679,7 +682,7 @@ raster_kernel(const RasterParams p) {
     ts.N = mk3(r2.y, r2.z, r2.w); ts.num = r3.x; ts.den = r3.y;
     float a, bq, c;
     // conservative early-z: r4.z is a lower bound of every depth key this triangle can produce
-    // (0.99 * min vertex depth, only for triangles with zmax <= 2 zmin); if even that is behind the
+    // (0.9985 * min vertex depth, only for triangles with zmax <= 2 zmin); if even that is behind the
     // pixel's current winner the pair cannot win (ties have equal keys and are never skipped)
     ZEntry cur = zt[q];
     const bool behind = (unsigned)(r4.z ^ 0x80000000) > (unsigned)(cur.key >> 32);
