@@ -501,7 +501,7 @@ struct RasterParams {
   const float* texture; const float* texcoords; const float* sh_coeff;
   float* bary; int32_t* face; float* render;
   unsigned long long* ctaTrace;
-  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, spanZ, role, pdl, grid2d, texBilinear;
+  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, spanZ, role, pdl, grid2d, texBilinear, resolvePrefetch;
   float cullMargin;
 };
 
@@ -900,6 +900,25 @@ raster_kernel(const RasterParams p) {
   const float4* vn = p.vnorm4 + (size_t)b * p.N;
   const float4* vc = p.vcol4 + (size_t)b * p.N;
   const bool doShade = (p.shading == GVV_SHADING_SHADED && p.albedo != GVV_ALBEDO_NORMAL) || p.albedo == GVV_ALBEDO_LIGHTING;
+  if (p.resolvePrefetch) {
+    // The resolve loop below walks a thread's pixels one after the other, each with a two-level dependent
+    // gather (face -> three vertex normals and colours).  A first sweep pulls those lines into L1 for all of the
+    // thread's pixels at once (prefetches need no destination registers), so the loop itself hits L1.
+    for (int q = qLo + tid; q < qHi; q += NTH) {
+      const unsigned long long key = zt[q].key;
+      if (key != kEmptyKey) {
+        const int4 fc = __ldg(p.faces4 + (int)(unsigned)(key & 0xffffffffull));
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(vn + fc.x));
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(vn + fc.y));
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(vn + fc.z));
+        if (p.albedo == GVV_ALBEDO_VERTEX_COLOR) {
+          asm volatile("prefetch.global.L1 [%0];" :: "l"(vc + fc.x));
+          asm volatile("prefetch.global.L1 [%0];" :: "l"(vc + fc.y));
+          asm volatile("prefetch.global.L1 [%0];" :: "l"(vc + fc.z));
+        }
+      }
+    }
+  }
   for (int q = qLo + tid; q < qHi; q += NTH) {
     const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
     if (x >= p.W || y >= p.H) continue;
@@ -1084,7 +1103,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   p.texture = a.texture; p.texcoords = a.texcoords; p.sh_coeff = a.sh_coeff;
   p.bary = a.bary; p.face = a.face; p.render = a.render; p.ctaTrace = a.s.ctaTrace;
   p.C = a.C; p.N = a.N; p.F = a.F; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
-  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv; p.interleave = a.interleave; p.hiz = a.hiz; p.spanZ = a.spanZ; p.texBilinear = a.texBilinear;
+  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv; p.interleave = a.interleave; p.hiz = a.hiz; p.spanZ = a.spanZ; p.texBilinear = a.texBilinear; p.resolvePrefetch = a.resolvePrefetch;
   p.grid2d = nItems <= 65535 ? 1 : 0;
   const dim3 gridT = p.grid2d ? dim3((unsigned)V, (unsigned)nItems) : dim3((unsigned)nItems * (unsigned)V);
   tm->begin(K_RASTER, st);
