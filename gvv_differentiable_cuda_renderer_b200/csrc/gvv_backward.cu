@@ -103,6 +103,8 @@ struct PixelParams {
 
 constexpr int kVals = 27;
 constexpr int kShRows = 12;  // rows 27..38 of the warp buffer: g*albedo (3) and the SH basis (9) of every pixel, for the SH gradient
+constexpr int kWarpBufFloats = (27 + 12 + 3) * 36;
+constexpr int kIdRows = 3;   // rows 39..41: the three vertex ids of every pixel's triangle (int bits), read at the end of a run
 constexpr int kRow = 36;    // 32 pixels + 4 pad: a quarter-warp's float4 reads of 8 different rows hit 32 different banks
 
 // Tolerance-level arithmetic of the backward: reciprocal-multiply instead of IEEE divides
@@ -149,7 +151,7 @@ constexpr int kSlabs = 4;
 
 __global__ void __launch_bounds__(256, 4)
 pixel_grad_kernel(const PixelParams p) {
-  __shared__ __align__(16) float buf[8][(kVals + kShRows) * kRow];   // per warp: value-major, kRow floats per value (32 pixels + pad)
+  extern __shared__ __align__(16) float buf_dyn[];   // per warp: (kVals + kShRows + kIdRows) rows, value-major, kRow floats per value (32 pixels + pad)
   __shared__ float shPart[8][kVals];
   __shared__ CamRec cam;
   __shared__ float shc[27];
@@ -173,7 +175,7 @@ pixel_grad_kernel(const PixelParams p) {
   if (tid >= 64 && tid < 64 + 27) shc[tid - 64] = __ldg(p.sh_coeff + (size_t)view * 27 + (tid - 64));
   if (__syncthreads_or(any) == 0) return;
 
-  float* mybuf = buf[warp];
+  float* mybuf = buf_dyn + warp * kWarpBufFloats;
   float* mine = mybuf + lane;   // value j of this lane's pixel lives at mine[j * kRow]
   float shsum = 0.f;            // lane j < 27: SH gradient (ch,k) summed over this warp's segments
 
@@ -198,6 +200,9 @@ pixel_grad_kernel(const PixelParams p) {
       const float2 ab = __ldg(reinterpret_cast<const float2*>(p.bary) + pix);
       const float bc[3] = {ab.x, ab.y, 1.f - ab.x - ab.y};
       const int4 fc = __ldg(p.faces4 + face);
+      mine[(kVals + kShRows + 0) * kRow] = __int_as_float(fc.x);   // vertex ids for the run-end atomics of the scatter stage
+      mine[(kVals + kShRows + 1) * kRow] = __int_as_float(fc.y);
+      mine[(kVals + kShRows + 2) * kRow] = __int_as_float(fc.z);
       const float4* pos = p.pos4 + (size_t)b * p.N;
       const float4* nor = p.nor4 + (size_t)view * p.N;
       const V3 p0 = ld4(pos, fc.x), p1 = ld4(pos, fc.y), p2 = ld4(pos, fc.z);
@@ -370,6 +375,7 @@ pixel_grad_kernel(const PixelParams p) {
     // warp-uniform, so the 32 steps are unrolled with uniform branches; pixels outside a run may hold
     // stale data -- it is discarded by the reset at the next head.
     const float4* row = reinterpret_cast<const float4*>(mybuf + (lane < kVals ? lane : 0) * kRow);
+    const float* idrow = mybuf + (kVals + kShRows + vi) * kRow;
     float acc = 0.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
@@ -380,10 +386,8 @@ pixel_grad_kernel(const PixelParams p) {
         const int l = 4 * g + u;
         acc = ((head >> l) & 1u) ? vv[u] : acc + vv[u];
         if ((endm >> l) & 1u) {
-          const int fr = __shfl_sync(FULL_MASK, face, l);
           if (active && acc != 0.f) {
-            const int4 fc = __ldg(p.faces4 + fr);
-            const int vid = vi == 0 ? fc.x : (vi == 1 ? fc.y : fc.z);
+            const int vid = __float_as_int(idrow[l]);        // vertex vi of the triangle pixel l sees (one shared-memory read)
             atomicAdd(base + (size_t)vid * vstride, acc);
           }
         }
@@ -523,7 +527,10 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   p.C = a.C; p.N = a.N; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
   p.albedo = a.albedo; p.shading = a.shading; p.imgFilter = a.imgFilter; p.texBilinear = a.texBilinear;
   tm->begin(K_PIXEL_GRAD, st);
-  pixel_grad_kernel<<<dim3((a.W + 31) / 32, (a.H + 31) / 32, V), 256, 0, st>>>(p);
+  constexpr int kPixelSmem = 8 * kWarpBufFloats * (int)sizeof(float);
+  static bool pgAttr = false;
+  if (!pgAttr) { cudaFuncSetAttribute(pixel_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPixelSmem); pgAttr = true; }
+  pixel_grad_kernel<<<dim3((a.W + 31) / 32, (a.H + 31) / 32, V), 256, kPixelSmem, st>>>(p);
   tm->end(st);
   ++launches;
   if (a.shading == GVV_SHADING_SHADED) {
