@@ -356,6 +356,10 @@ pixel_grad_kernel(const PixelParams p) {
       }
 #pragma unroll
       for (int j = 0; j < 9; ++j) mine[(9 + j) * kRow] = pos9[j];
+    } else if (cv != FULL_MASK) {
+      // pixels that see no triangle contribute zeros, so that the scatter stage can add every pixel of the row
+#pragma unroll
+      for (int j = 0; j < kVals; ++j) mine[j * kRow] = 0.f;
     }
 
     // ---- run-aggregated scatter: lane j owns value j ----
@@ -370,10 +374,9 @@ pixel_grad_kernel(const PixelParams p) {
     float* base = arr == 0 ? p.vcol_grad : (arr == 1 ? p.vpos_grad : p.gnorm);
     const int vstride = arr == 2 ? 4 : 3;          // gnorm is float4-strided for aligned gathers in normal_term_kernel
     base += (size_t)b * p.N * vstride + comp;
-    // Lane j walks row j (the 32 pixels' value j) with a segmented running sum: reset at the head
-    // of every run of equal face id, flushed with ONE warp-wide atomic at its end.  head/endm are
-    // warp-uniform, so the 32 steps are unrolled with uniform branches; pixels outside a run may hold
-    // stale data -- it is discarded by the reset at the next head.
+    // Lane j walks row j (the 32 pixels' value j) with a segmented running sum: flushed with ONE
+    // warp-wide atomic at the end of every run of equal face id and reset to zero there (pixels outside
+    // a run hold zeros).  endm is warp-uniform, so the 32 steps are unrolled with uniform branches.
     const float4* row = reinterpret_cast<const float4*>(mybuf + (lane < kVals ? lane : 0) * kRow);
     const float* idrow = mybuf + (kVals + kShRows + vi) * kRow;
     float acc = 0.f;
@@ -384,12 +387,13 @@ pixel_grad_kernel(const PixelParams p) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int l = 4 * g + u;
-        acc = ((head >> l) & 1u) ? vv[u] : acc + vv[u];
+        acc += vv[u];
         if ((endm >> l) & 1u) {
           if (active && acc != 0.f) {
             const int vid = __float_as_int(idrow[l]);        // vertex vi of the triangle pixel l sees (one shared-memory read)
             atomicAdd(base + (size_t)vid * vstride, acc);
           }
+          acc = 0.f;
         }
       }
     }
