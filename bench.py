@@ -126,9 +126,14 @@ def run_ours(args, rank, world, local_rank):
         k, v = kv.split("=")
         r.set_option(k, int(v))
 
+    # the gradients of the parameters shared across ranks (SH, colours) are written back to back into one flat
+    # buffer, so that the per-step collective is ONE in-place all-reduce without pack / unpack kernels
+    _, (gsh_out, gcol_out) = sharding.shared_grad_buffer([(1, C, 27), (1, N, 3)], dev)
+
     def step():
         bary, face, render, vn, _, _ = r.forward(*ins)
-        gpos, gcol, gtex, gsh = r.backward(G, None, ins[0], ins[1], ins[2], ins[3], ins[4], vn, bary, face, ins[5], ins[6])
+        gpos, gcol, gtex, gsh = r.backward(G, None, ins[0], ins[1], ins[2], ins[3], ins[4], vn, bary, face, ins[5], ins[6],
+                                           out=(None, gcol_out, None, gsh_out))
         if world > 1:
             sharding.allreduce_shared_grads([gsh, gcol])
         return gpos

@@ -210,7 +210,10 @@ class NativeRenderer:
         return bary, face, render, vnormal, target_out, normal_map
 
     def backward(self, render_grad, target_grad, vertex_pos, vertex_color, texture, sh_coeff, target_image,
-                 vertex_normal, bary, face, extrinsics, intrinsics):
+                 vertex_normal, bary, face, extrinsics, intrinsics, out=None):
+        """out: optional preallocated (vertex_pos_grad, vertex_color_grad, texture_grad, sh_coeff_grad) fp32 contiguous
+        tensors (entries may be None) -- e.g. views into ONE flat buffer, so that the gradients of parameters shared
+        across ranks can be all-reduced in place without packing (sharding.allreduce_shared_grads)."""
         dev = self.device
         B, texH, texW = int(texture.shape[0]), int(texture.shape[1]), int(texture.shape[2])
         C, N = self.C, self.N
@@ -224,10 +227,16 @@ class NativeRenderer:
         intrinsics = _f32(intrinsics, "intrinsics", dev)
         o = dict(device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
-            gpos = torch.empty((B, N, 3), **o)
-            gcol = torch.empty((B, N, 3), **o)
-            gtex = torch.empty((B, texH, texW, 3), **o)
-            gsh = torch.empty((B, C, 27), **o)
+            pre = tuple(out) if out is not None else (None, None, None, None)
+            shapes = ((B, N, 3), (B, N, 3), (B, texH, texW, 3), (B, C, 27))
+            outs = []
+            for t, shp, name in zip(pre, shapes, ("vertex_pos_grad", "vertex_color_grad", "texture_grad", "sh_coeff_grad")):
+                if t is None:
+                    t = torch.empty(shp, **o)
+                elif t.device != dev or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != int(np.prod(shp)):
+                    raise GvvError(f"out[{name}] must be a contiguous fp32 tensor of {shp} on {dev}")
+                outs.append(t)
+            gpos, gcol, gtex, gsh = outs
             _check(lib().gvv_backward(self._h, B, texH, texW, *[_ptr(a) for a in args], _ptr(face), _ptr(target_grad),
                                       _ptr(extrinsics), _ptr(intrinsics), _ptr(gpos), _ptr(gcol), _ptr(gtex),
                                       _ptr(gsh), self._stream()), "gvv_backward")

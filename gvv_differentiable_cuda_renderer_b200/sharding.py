@@ -46,6 +46,15 @@ def allreduce_shared_grads(grads, group=None, async_op=False):
     all-reduced, and unpacked in place.  Returns a handle with .wait() when async_op."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return _Done()
+    flat = _common_flat_buffer(grads)
+    if flat is not None:
+        # the gradients already live back to back in one buffer (NativeRenderer.backward(out=...) with views of
+        # shared_grad_buffer): one in-place collective, no pack / unpack kernels
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        h = _Pending(work.wait)
+        if not async_op:
+            h.wait()
+        return h
     flat = torch.cat([g.reshape(-1).to(torch.float32) for g in grads])
     work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
 
@@ -61,6 +70,32 @@ def allreduce_shared_grads(grads, group=None, async_op=False):
     if not async_op:
         h.wait()
     return h
+
+
+def shared_grad_buffer(shapes, device):
+    """One flat fp32 buffer + a view per shape, laid out back to back: pass the views as `out=` of the backward
+    and the list of views to allreduce_shared_grads, which then reduces the buffer in place."""
+    sizes = [int(torch.Size(s).numel()) for s in shapes]
+    flat = torch.empty(sum(sizes), dtype=torch.float32, device=device)
+    views, off = [], 0
+    for s, n in zip(shapes, sizes):
+        views.append(flat[off:off + n].view(s))
+        off += n
+    return flat, views
+
+
+def _common_flat_buffer(grads):
+    """The flat tensor the gradients are consecutive views of, or None."""
+    if not grads or any(g.dtype != torch.float32 or not g.is_contiguous() for g in grads):
+        return None
+    st = grads[0].untyped_storage()
+    off = grads[0].storage_offset()
+    start = off
+    for g in grads:
+        if g.untyped_storage().data_ptr() != st.data_ptr() or g.storage_offset() != off:
+            return None
+        off += g.numel()
+    return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st, start, (off - start,))
 
 
 class _Done:

@@ -70,6 +70,14 @@ def _worker(rank, world, port, B, q):
         h = sharding.allreduce_shared_grads([g_sh, g_v], async_op=True)
         h.wait()
         ok1 = torch.allclose(g_sh, full["sh_coeff"].sum(0)) and torch.allclose(g_v, full["vertex_pos"].sum(0))
+        # the same through ONE flat buffer (views handed to the backward as out=): reduced in place, no packing
+        flat, (f_sh, f_v) = sharding.shared_grad_buffer([(2, 27), (4, 3)], "cpu")
+        f_sh.copy_(loc["sh_coeff"].sum(0)); f_v.copy_(loc["vertex_pos"].sum(0))
+        assert sharding._common_flat_buffer([f_sh, f_v]).data_ptr() == flat.data_ptr()
+        assert sharding._common_flat_buffer([f_v, f_sh]) is None and sharding._common_flat_buffer([g_sh, g_v]) is None
+        sharding.allreduce_shared_grads([f_sh, f_v])
+        ok1 = ok1 and torch.allclose(f_sh, full["sh_coeff"].sum(0)) and torch.allclose(f_v, full["vertex_pos"].sum(0))
+        ok1 = ok1 and torch.allclose(flat[:54], full["sh_coeff"].sum(0).reshape(-1))
         # per-batch-element rows are disjoint: gather restores the full batch in order
         gathered = sharding.gather_batch(loc["sh_coeff"] * 2.0, B)
         ok2 = torch.equal(gathered, full["sh_coeff"] * 2.0)
