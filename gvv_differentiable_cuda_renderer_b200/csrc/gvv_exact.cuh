@@ -75,6 +75,8 @@ __device__ __forceinline__ void fill_camrec(const float* __restrict__ extr, cons
   const float oz = __fdiv_rn(Einv[11], Einv[15]);
   r.ro[0] = ox; r.ro[1] = oy; r.ro[2] = oz;
   r.ros[0] = __fdiv_rn(ox, 1000.f); r.ros[1] = __fdiv_rn(oy, 1000.f); r.ros[2] = __fdiv_rn(oz, 1000.f);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) r.pad[i] = 0.f;   // the record is copied whole into shared memory by its readers
 }
 
 // Reference: getRayCuda2 + backprojectPixelCuda (CameraUtil.h:223-236,251-258).
