@@ -451,3 +451,35 @@ def test_forward_backward_are_cuda_graph_capturable():
     assert torch.equal(face, face0) and not torch.equal(render, render0)
     del graph
     r.close()
+
+
+OPTION_SETS = [
+    {"hiz": 0}, {"span_z": 0}, {"span_z": 1}, {"hiz": 0, "span_z": 0, "cull_margin_milli": 250},
+    {"split_unit": 48}, {"split_unit": 16, "hiz": 0}, {"heavy_mode": 2, "heavy_thr": 32}, {"heavy_mode": 2, "heavy_thr": 32, "heavy_slots": 3},
+    {"heavy_mode": 0}, {"spread_empty": 1}, {"spread_empty": 1, "split_unit": 32}, {"cta_threads": 128}, {"tile": 16}, {"tile": 16, "split_unit": 24},
+    {"interleave": 0}, {"batch_div": 3}, {"batch_div": 24}, {"ray_cache": 1}, {"resolve_prefetch": 1},
+]
+
+
+@pytest.mark.parametrize("opts", OPTION_SETS, ids=[",".join(f"{k}={v}" for k, v in o.items()) for o in OPTION_SETS])
+def test_every_tuning_knob_keeps_the_bits(opts):
+    """All scheduling / culling knobs of gvv_set_option only change WHO evaluates a (pixel, triangle) pair or
+    whether a pair that provably cannot win is evaluated at all: face, barycentric and render buffers must be
+    bit-identical to the configuration that tests every bbox pixel in one pass (the reference's schedule)."""
+    sc = synthetic.make_scene(kind="sphere", rings=60, segments=64, cameras=3, width=200, height=168, tex=16, seed=8)
+    ins = [T(sc[k]) for k in INPUT_KEYS]
+    base = make(sc, "vertexColor", "shaded")
+    for k, v in {"cull_margin_milli": -1, "hiz": 0, "span_z": 0, "heavy_mode": 0}.items():
+        base.set_option(k, v)
+    b0, f0, r0, v0, _, _ = base.forward(*ins)
+    r = make(sc, "vertexColor", "shaded", tile=opts.get("tile", 32))
+    for k, v in opts.items():
+        if k != "tile":
+            r.set_option(k, v)
+    for _ in range(2):                                   # twice: the self-cleaning scratch must be back in its initial state
+        b1, f1, r1, v1, _, _ = r.forward(*ins)
+        assert torch.equal(f1, f0)
+        assert torch.equal(b1.view(torch.int32), b0.view(torch.int32))
+        assert torch.equal(r1.view(torch.int32), r0.view(torch.int32))
+        assert torch.equal(v1, v0)
+    base.close(); r.close()
