@@ -61,6 +61,7 @@ with open(os.path.join(ROOT, "profiles", "r01_ncu_summaries.md"), "a") as f:
         short = "raster_kernel" if "raster_kernel" in name else ("pixel_grad_kernel" if "pixel_grad" in name else None)
         if short:
             traffic[short] = int(byts("dram__bytes_read.sum") + byts("dram__bytes_write.sum"))
+            traffic[short + "_warp_inst"] = int(float(d["smsp__inst_executed.sum"].replace(",", "")))
 if traffic:
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print("wrote", tag, traffic)
