@@ -151,6 +151,7 @@ constexpr int kSlabs = 4;
 
 __global__ void __launch_bounds__(256, 4)
 pixel_grad_kernel(const PixelParams p) {
+  chain_wait(); chain_trigger();
   extern __shared__ __align__(16) float buf_dyn[];   // per warp: (kVals + kShRows + kIdRows) rows, value-major, kRow floats per value (32 pixels + pad)
   __shared__ float shPart[8][kVals];
   __shared__ CamRec cam;
@@ -445,6 +446,7 @@ struct PrepArgs {
 };
 
 __global__ void prep_kernel(PrepArgs a) {
+  chain_wait(); chain_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t0 < a.V) fill_camrec(a.extr, a.intr, a.cams, (int)t0);   // camera records for pixel_grad_kernel (ref :17-61)
@@ -478,6 +480,7 @@ __global__ void prep_kernel(PrepArgs a) {
 __global__ void __launch_bounds__(256)
 normal_term_kernel(const float4* __restrict__ pos4, const float4* __restrict__ gnorm4, const int4* __restrict__ faces4,
                    float* __restrict__ vpos_grad, int N, int F) {
+  chain_wait(); chain_trigger();
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (f >= F) return;
@@ -519,7 +522,7 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   pa.nBN = (long long)a.B * a.N; pa.nVN = (long long)V * a.N;
   pa.extr = a.extrinsics; pa.intr = a.intrinsics; pa.cams = a.s.cams; pa.V = V;
   tm->begin(K_ZERO, st);
-  prep_kernel<<<148 * 8, 256, 0, st>>>(pa);
+  launch_chained(a.chain, prep_kernel, dim3(148 * 8), dim3(256), 0, st, pa);
   tm->end(st);
   ++launches;
   PixelParams p;
@@ -534,13 +537,13 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   constexpr int kPixelSmem = 8 * kWarpBufFloats * (int)sizeof(float);
   static bool pgAttr = false;
   if (!pgAttr) { cudaFuncSetAttribute(pixel_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPixelSmem); pgAttr = true; }
-  pixel_grad_kernel<<<dim3((a.W + 31) / 32, (a.H + 31) / 32, V), 256, kPixelSmem, st>>>(p);
+  launch_chained(a.chain, pixel_grad_kernel, dim3((a.W + 31) / 32, (a.H + 31) / 32, V), dim3(256), kPixelSmem, st, p);
   tm->end(st);
   ++launches;
   if (a.shading == GVV_SHADING_SHADED) {
     tm->begin(K_NORMAL_TERM, st);
-    normal_term_kernel<<<dim3((a.F + 255) / 256, a.B), 256, 0, st>>>(a.s.bpos4, reinterpret_cast<const float4*>(a.s.gnorm), a.faces4,
-                                                                    a.vpos_grad, a.N, a.F);
+    launch_chained(a.chain, normal_term_kernel, dim3((a.F + 255) / 256, a.B), dim3(256), 0, st, a.s.bpos4, reinterpret_cast<const float4*>(a.s.gnorm), a.faces4,
+                   a.vpos_grad, a.N, a.F);
     tm->end(st);
     ++launches;
   }

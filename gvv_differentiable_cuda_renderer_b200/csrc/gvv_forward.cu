@@ -44,6 +44,7 @@ __device__ __forceinline__ F3 ld3(const float* __restrict__ p, int i) {
 // face normals cross(v1-v0, v2-v0), world space, once per batch element (ref :122-141 computes them C times)
 __global__ void __launch_bounds__(256)
 face_normal_kernel(const float* __restrict__ vertex_pos, const int4* __restrict__ faces4, float4* __restrict__ fnorm4, int N, int F) {
+  chain_wait(); chain_trigger();
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (f >= F) return;
@@ -64,6 +65,7 @@ vertex_kernel(const float* __restrict__ vertex_pos, const float* __restrict__ ve
               float4* __restrict__ proj, float4* __restrict__ vscaled,
               float4* __restrict__ vnorm4, float4* __restrict__ vcol4, float* __restrict__ vertex_normal_out,
               int N, int F, int C) {
+  chain_wait(); chain_trigger();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int view = blockIdx.y, b = view / C, c = view - b * C;
   if (blockIdx.x == 0 && threadIdx.x == 0) bigCount[view] = 0;   // consumed by bin_count_kernel (next launch)
@@ -178,6 +180,7 @@ bin_count_kernel(const int4* __restrict__ faces4, const float4* __restrict__ pro
                  int* __restrict__ tileMinK, int* __restrict__ tileMaxK,
                  int* __restrict__ bigCount, int* __restrict__ bigList, int F, int N, int W, int H, int tileShift,
                  int tilesX, int nT) {
+  chain_wait(); chain_trigger();
   extern __shared__ int hist[];   // SMEM_HIST: hist[nT], mn[nT], mx[nT]
   int* mn = hist + nT;
   int* mx = hist + 2 * nT;
@@ -240,6 +243,7 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
                                                         int heavyThr, int heavySlots, int heavyLoad, int spreadEmpty,
                                                         const float* __restrict__ extr, const float* __restrict__ intr,
                                                         CamRec* __restrict__ cams) {
+  chain_wait(); chain_trigger();
   __shared__ int warpSum[32];
   __shared__ int carry;
   __shared__ int bucketStart[33], bucketFill[33];
@@ -343,6 +347,7 @@ bin_fill_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj
                 const int* __restrict__ tileCount, const int* __restrict__ tileThr,
                 int* __restrict__ tileCursor, int* __restrict__ tileCursorFar, int* __restrict__ bins, int F, int N, int W, int H, int tileShift,
                 int tilesX, int nT) {
+  chain_wait(); chain_trigger();
   extern __shared__ int sm[];   // SMEM_HIST: histN[nT], histF[nT], baseN[nT], baseF[nT]
   int* histN = sm;
   int* histF = sm + nT;
@@ -580,8 +585,12 @@ raster_kernel(const RasterParams p) {
   // item = tx | ty << 12 | strip << 24 | log2(K) << 27 | heavy << 29: this CTA owns rows [rowLo, rowLo + rowN) of tile (tx, ty)
   const int view = p.grid2d ? (int)blockIdx.x : (int)(blockIdx.x % p.V);
   const int rank = p.grid2d ? (int)blockIdx.y : (int)(blockIdx.x / p.V);
+  // heavy launch (role 1): wait for the binning, then let the 256-thread launch start beside this one.  The
+  // 256-thread launch waits for its predecessor itself unless that is the heavy launch (p.pdl), whose CTAs
+  // only trigger after their own wait -- so the binning is complete either way.
+  if (p.role == 1 || !p.pdl) chain_wait();
+  chain_trigger();
   const int item = p.tileOrder[(size_t)view * p.nItems + rank];
-  if (p.role == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // heavy launch: lets the 256-thread launch start beside it
   // The 256-thread launch may FINISH before the heavy one; whatever follows in the stream only waits for this
   // launch, so its last CTA (scheduled last) does not leave before the heavy launch has completed and flushed.
   if (p.role == 0 && p.pdl && blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1) asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1036,11 +1045,9 @@ int launch_camera(const float* extr, const float* intr, CamRec* cams, int* bigCo
 }
 
 int launch_vertex(const FwdArgs& a, cudaStream_t st) {
-  if (a.F > 0) face_normal_kernel<<<dim3((a.F + 255) / 256, a.B), 256, 0, st>>>(a.vertex_pos, a.faces4, a.s.fnorm4, a.N, a.F);
-  vertex_kernel<<<dim3((a.N + 127) / 128, a.B * a.C), 128, 0, st>>>(a.vertex_pos, a.vertex_color, a.s.fnorm4, a.vfOffsets, a.vfList,
-                                                             a.extrinsics, a.intrinsics, a.s.bigCount,
-                                                             a.s.proj, a.s.vscaled, a.s.vnorm4, a.s.vcol4,
-                                                             a.vertex_normal, a.N, a.F, a.C);
+  if (a.F > 0) launch_chained(a.chain, face_normal_kernel, dim3((a.F + 255) / 256, a.B), dim3(256), 0, st, a.vertex_pos, a.faces4, a.s.fnorm4, a.N, a.F);
+  launch_chained(a.chain, vertex_kernel, dim3((a.N + 127) / 128, a.B * a.C), dim3(128), 0, st, a.vertex_pos, a.vertex_color, a.s.fnorm4, a.vfOffsets, a.vfList,
+                 a.extrinsics, a.intrinsics, a.s.bigCount, a.s.proj, a.s.vscaled, a.s.vnorm4, a.s.vcol4, a.vertex_normal, a.N, a.F, a.C);
   return a.F > 0 ? 2 : 1;
 }
 
@@ -1054,11 +1061,11 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const dim3 gridF((a.F + 256 * kBinFacesPerThread - 1) / (256 * kBinFacesPerThread), V);
   tm->begin(K_BIN_COUNT, st);
   if (a.nT <= kSmemHistTiles) {
-    bin_count_kernel<true><<<gridF, 256, 3 * a.nT * sizeof(int), st>>>(a.faces4, a.s.proj, a.s.tileCount, a.s.tileMinK, a.s.tileMaxK,
-                                                                      a.s.bigCount, a.s.bigList, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
+    launch_chained(a.chain, bin_count_kernel<true>, gridF, dim3(256), 3 * a.nT * sizeof(int), st, a.faces4, a.s.proj, a.s.tileCount, a.s.tileMinK, a.s.tileMaxK,
+                   a.s.bigCount, a.s.bigList, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
   } else {
-    bin_count_kernel<false><<<gridF, 256, 0, st>>>(a.faces4, a.s.proj, a.s.tileCount, a.s.tileMinK, a.s.tileMaxK,
-                                                  a.s.bigCount, a.s.bigList, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
+    launch_chained(a.chain, bin_count_kernel<false>, gridF, dim3(256), 0, st, a.faces4, a.s.proj, a.s.tileCount, a.s.tileMinK, a.s.tileMaxK,
+                   a.s.bigCount, a.s.bigList, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
   }
   tm->end(st);
   ++launches;
@@ -1078,21 +1085,20 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const bool fewViews = (smCount / 4) / max(V, 1) >= 16 || a.heavyMode == 2;
   const bool useHeavy = a.heavyMode > 0 && a.heavyThr > 0 && a.tile == 32 && !a.rayCache && a.ctaThreads == 256 && fewViews;
   const int maxLog = a.splitUnit > 0 ? (a.tile == 32 ? 3 : 2) : 0;
-  bin_scan_kernel<<<V, 1024, 0, st>>>(a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.s.tileMinK, a.s.tileMaxK, a.s.tileThr, a.nT, a.tilesX, nItems, a.splitUnit > 0 ? a.splitUnit : 1, maxLog,
-                                      useHeavy ? a.heavyThr : 0, kHeavySlots, a.heavyMode == 2 ? -1 : max(1, a.ctaSlots / V), a.spreadEmpty, a.extrinsics, a.intrinsics, a.s.cams);
+  launch_chained(a.chain, bin_scan_kernel, dim3(V), dim3(1024), 0, st, a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.s.tileMinK, a.s.tileMaxK, a.s.tileThr,
+                 a.nT, a.tilesX, nItems, a.splitUnit > 0 ? a.splitUnit : 1, maxLog,
+                 useHeavy ? a.heavyThr : 0, kHeavySlots, a.heavyMode == 2 ? -1 : max(1, a.ctaSlots / V), a.spreadEmpty, a.extrinsics, a.intrinsics, a.s.cams);
   tm->end(st);
   ++launches;
   tm->begin(K_BIN_FILL, st);
   if (a.nT <= kSmemHistTiles) {
     static bool fillAttr = false;
     if (!fillAttr) { cudaFuncSetAttribute(bin_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSmemHistTiles * (int)sizeof(int)); fillAttr = true; }
-    bin_fill_kernel<true><<<gridF, 256, 4 * a.nT * sizeof(int), st>>>(a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCount, a.s.tileThr,
-                                                                     a.s.tileCursor, a.s.tileCursorFar, a.s.bins,
-                                                                     a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
+    launch_chained(a.chain, bin_fill_kernel<true>, gridF, dim3(256), 4 * a.nT * sizeof(int), st, a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCount, a.s.tileThr,
+                   a.s.tileCursor, a.s.tileCursorFar, a.s.bins, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
   } else {
-    bin_fill_kernel<false><<<gridF, 256, 0, st>>>(a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCount, a.s.tileThr,
-                                                 a.s.tileCursor, a.s.tileCursorFar, a.s.bins,
-                                                 a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
+    launch_chained(a.chain, bin_fill_kernel<false>, gridF, dim3(256), 0, st, a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCount, a.s.tileThr,
+                   a.s.tileCursor, a.s.tileCursorFar, a.s.bins, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
   }
   tm->end(st);
   ++launches;
@@ -1125,7 +1131,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   if (useHeavy) {
     RasterParams ph = p;
     ph.role = 1; ph.pdl = 0;
-    raster_kernel<32, false, 1024><<<(p.grid2d ? dim3((unsigned)V, (unsigned)kHeavySlots) : dim3((unsigned)kHeavySlots * (unsigned)V)), 1024, raster_smem_bytes<32, false, 1024>(), st>>>(ph);
+    launch_chained(a.chain, raster_kernel<32, false, 1024>, (p.grid2d ? dim3((unsigned)V, (unsigned)kHeavySlots) : dim3((unsigned)kHeavySlots * (unsigned)V)), dim3(1024), raster_smem_bytes<32, false, 1024>(), st, ph);
     ++launches;
   }
   p.role = 0; p.pdl = useHeavy ? 1 : 0;
@@ -1135,7 +1141,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = useHeavy ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = (useHeavy || a.chain) ? 1 : 0;
 #define GVV_RASTER_LAUNCH(TS, RC, NTH) do { cfg.blockDim = dim3(NTH); cfg.dynamicSmemBytes = raster_smem_bytes<TS, RC, NTH>(); \
                                             cudaLaunchKernelEx(&cfg, raster_kernel<TS, RC, NTH>, p); } while (0)
     if (a.tile == 16) {

@@ -65,6 +65,7 @@ struct gvv_renderer {
   int albedo = 0, shading = 0, imgFilter = 1, texFilter = 1, computeNormalMap = 0;
   int tile = 32, tilesX = 0, tilesY = 0, nT = 0;
   const float* targetDu = nullptr; const float* targetDv = nullptr;   // caller-owned precomputed target-image gradient (gvv_set_target_gradient)
+  int chain = 1;              // launch the kernels of a call as a programmatic dependent-launch chain
   int resolvePrefetch = 0;    // raster: L1 prefetch sweep of the resolve stage's vertex gathers (measured slower: 0.272 -> 0.282 ms)
   int texBilinear = 0;        // non-default: bilinear texture fetch + weighted 4-texel gradient scatter (the variants the reference has commented out)
   int spreadEmpty = 0;        // raster: interleave the (HBM-bound) empty tiles with the (ALU-bound) non-empty ones
@@ -97,7 +98,7 @@ namespace gvv {
 
 struct FwdArgs {
   int B, C, N, F, W, H, texH, texW, albedo, shading;
-  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, spanZ, splitUnit, heavyThr, heavyMode, heavySlots, ctaSlots, spreadEmpty, texBilinear, resolvePrefetch;
+  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, spanZ, splitUnit, heavyThr, heavyMode, heavySlots, ctaSlots, spreadEmpty, texBilinear, resolvePrefetch, chain;
   float cullMargin;
   const float *vertex_pos, *vertex_color, *texture, *sh_coeff, *extrinsics, *intrinsics;
   const float* texcoords;
@@ -108,7 +109,7 @@ struct FwdArgs {
 };
 
 struct BwdArgs {
-  int B, C, N, F, W, H, texH, texW, albedo, shading, imgFilter, texBilinear;
+  int B, C, N, F, W, H, texH, texW, albedo, shading, imgFilter, texBilinear, chain;
   const float *render_grad, *target_grad, *vertex_pos, *vertex_color, *texture, *sh_coeff, *target_image,
       *vertex_normal, *bary, *extrinsics, *intrinsics, *texcoords, *target_du, *target_dv;
   const int32_t* face;
@@ -117,6 +118,26 @@ struct BwdArgs {
   float *vpos_grad, *vcol_grad, *tex_grad, *sh_grad;
   Scratch s;
 };
+
+// Programmatic dependent launch (sm_90+): every kernel of a call is launched with the programmatic-stream-
+// serialization attribute and starts with chain_wait() (= wait until the preceding kernel of the stream has
+// completed and flushed) followed by chain_trigger() (= the next kernel may be scheduled as soon as all CTAs of
+// this one are resident or gone).  Semantics are those of plain stream order; what overlaps is the launch latency
+// and CTA ramp-up of a kernel with the tail of its predecessor -- a few microseconds per boundary, which is what
+// the small kernels of this pipeline cost.
+__device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void chain_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(bool chained, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = chained ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // Each returns the number of kernels launched, or -1 after a launch error.
 int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm);
