@@ -106,14 +106,23 @@ vertex_kernel(const float* __restrict__ vertex_pos, const float* __restrict__ ve
     fans &= fans - 1;
     const int hb = __shfl_sync(FULL_MASK, beg, L), he = __shfl_sync(FULL_MASK, end, L);
     F3 acc = mk3(0.f, 0.f, 0.f);
-    for (int c0 = hb; c0 < he; c0 += 32) {
-      float4 fn = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c0 + lane < he) fn = __ldg(fnb + __ldg(vfList + c0 + lane));
-      const int cnt = min(32, he - c0);
-      for (int k = 0; k < cnt; ++k) {
-        const float fx = __shfl_sync(FULL_MASK, fn.x, k), fy = __shfl_sync(FULL_MASK, fn.y, k), fz = __shfl_sync(FULL_MASK, fn.z, k);
-        if (c0 + k == hb) acc = mk3(fx, fy, fz);
-        else acc = mk3(__fadd_rn(acc.x, fx), __fadd_rn(acc.y, fy), __fadd_rn(acc.z, fz));
+    for (int g0 = hb; g0 < he; g0 += 32 * 4) {          // four chunks of 32 incident faces in flight at a time
+      float4 fn[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = g0 + 32 * c + lane;
+        fn[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < he) fn[c] = __ldg(fnb + __ldg(vfList + i));
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int c0 = g0 + 32 * c;
+        const int cnt = min(32, he - c0);
+        for (int k = 0; k < cnt; ++k) {
+          const float fx = __shfl_sync(FULL_MASK, fn[c].x, k), fy = __shfl_sync(FULL_MASK, fn[c].y, k), fz = __shfl_sync(FULL_MASK, fn[c].z, k);
+          if (c0 + k == hb) acc = mk3(fx, fy, fz);
+          else acc = mk3(__fadd_rn(acc.x, fx), __fadd_rn(acc.y, fy), __fadd_rn(acc.z, fz));
+        }
       }
     }
     if (lane == L) nrm = acc;
@@ -729,9 +738,14 @@ raster_kernel(const RasterParams p) {
     if (!twoPass) break;
     __syncthreads();                                  // pass 0 complete
     unsigned m = 0u;
-    for (int q = qLo + tid; q < qHi; q += NTH) {
-      const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
-      if (x < p.W && y < p.H) m = max(m, (unsigned)(zt[q].key >> 32));
+    const unsigned* zhi = reinterpret_cast<const unsigned*>(zt) + 1;     // high word of every key
+    if (tileX0 + TS <= p.W && tileY0 + TS <= p.H) {                       // tile inside the image: no per-pixel bounds test
+      for (int q = qLo + tid; q < qHi; q += NTH) m = max(m, zhi[4 * q]);
+    } else {
+      for (int q = qLo + tid; q < qHi; q += NTH) {
+        const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
+        if (x < p.W && y < p.H) m = max(m, zhi[4 * q]);
+      }
     }
     m = __reduce_max_sync(FULL_MASK, m);
     if (lane == 0) atomicMax(&sZmax, m);
