@@ -251,8 +251,16 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
                                                         int nT, int tilesX, int nItems, int splitUnit, int maxLog,
                                                         int heavyThr, int heavySlots, int heavyLoad, int spreadEmpty,
                                                         const float* __restrict__ extr, const float* __restrict__ intr,
-                                                        CamRec* __restrict__ cams) {
+                                                        CamRec* __restrict__ cams, int numViews) {
   chain_wait(); chain_trigger();
+  // blocks beyond the views: the camera records (E^-1, (KE)^-1, ray origin) of all views, one thread each, beside
+  // the scans instead of after them -- the reference spends a <<<1,1>>> launch with a serial loop on this
+  if ((int)blockIdx.x >= numViews) {
+    const int v = ((int)blockIdx.x - numViews) * blockDim.x + threadIdx.x;
+    if (v < numViews) fill_camrec(extr, intr, cams, v);
+    return;
+  }
+  extern __shared__ int cnt[];   // the view's tile histogram, read four times below
   __shared__ int warpSum[32];
   __shared__ int carry;
   __shared__ int bucketStart[33], bucketFill[33];
@@ -260,10 +268,11 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
   const int view = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry = 0;
+  for (int i = threadIdx.x; i < nT; i += blockDim.x) cnt[i] = tileCount[(size_t)view * nT + i];
   __syncthreads();
   for (int base = 0; base < nT; base += blockDim.x) {
     const int i = base + threadIdx.x;
-    const int v = (i < nT) ? tileCount[(size_t)view * nT + i] : 0;
+    const int v = (i < nT) ? cnt[i] : 0;
     int x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL_MASK, x, o); if (lane >= o) x += y; }
@@ -297,7 +306,7 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
     __syncthreads();
     int extra = 0;
     for (int i = threadIdx.x; i < nT; i += blockDim.x)
-      extra += (1 << strip_log2(tileCount[(size_t)view * nT + i], unit, maxLog)) - 1;
+      extra += (1 << strip_log2(cnt[i], unit, maxLog)) - 1;
     if (extra) atomicAdd(&extraItems, extra);
     __syncthreads();
     const int total = extraItems;
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
   if (threadIdx.x < 33) { bucketStart[threadIdx.x] = 0; bucketFill[threadIdx.x] = 0; }
   __syncthreads();
   for (int i = threadIdx.x; i < nT; i += blockDim.x) {
-    const int c = tileCount[(size_t)view * nT + i];
+    const int c = cnt[i];
     const int l = strip_log2(c, unit, maxLog), w = c >> l;
     atomicAdd(&bucketStart[w > 0 ? 32 - __clz(w) : 0], 1 << l);
   }
@@ -322,7 +331,7 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
   __syncthreads();
   int* order = tileOrder + (size_t)view * nItems;
   for (int i = threadIdx.x; i < nT; i += blockDim.x) {
-    const int c = tileCount[(size_t)view * nT + i];
+    const int c = cnt[i];
     const int l = strip_log2(c, unit, maxLog), w = c >> l;
     const int k = w > 0 ? 32 - __clz(w) : 0;
     const int pos0 = bucketStart[k] + atomicAdd(&bucketFill[k], 1 << l);
@@ -345,9 +354,6 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
     }
   }
   for (int i = extraItems + threadIdx.x; i < nItems; i += blockDim.x) order[i] = -1;
-  // one block per view: its spare time also produces the view's camera record (E^-1, (KE)^-1, ray
-  // origin) for the raster kernel -- the reference spends a <<<1,1>>> launch on this
-  if (threadIdx.x == 0) fill_camrec(extr, intr, cams, view);
 }
 
 template <bool SMEM_HIST>
@@ -1099,9 +1105,12 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const bool fewViews = (smCount / 4) / max(V, 1) >= 16 || a.heavyMode == 2;
   const bool useHeavy = a.heavyMode > 0 && a.heavyThr > 0 && a.tile == 32 && !a.rayCache && a.ctaThreads == 256 && fewViews;
   const int maxLog = a.splitUnit > 0 ? (a.tile == 32 ? 3 : 2) : 0;
-  launch_chained(a.chain, bin_scan_kernel, dim3(V), dim3(1024), 0, st, a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.s.tileMinK, a.s.tileMaxK, a.s.tileThr,
+  static bool scanAttr = false;
+  if (!scanAttr) { cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); scanAttr = true; }
+  if ((size_t)a.nT * sizeof(int) > 160 * 1024) return -1;   // 40960 tiles = e.g. 6400 x 6400 pixels at 32 x 32; larger grids are not supported
+  launch_chained(a.chain, bin_scan_kernel, dim3(V + (V + 1023) / 1024), dim3(1024), a.nT * sizeof(int), st, a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.s.tileMinK, a.s.tileMaxK, a.s.tileThr,
                  a.nT, a.tilesX, nItems, a.splitUnit > 0 ? a.splitUnit : 1, maxLog,
-                 useHeavy ? a.heavyThr : 0, kHeavySlots, a.heavyMode == 2 ? -1 : max(1, a.ctaSlots / V), a.spreadEmpty, a.extrinsics, a.intrinsics, a.s.cams);
+                 useHeavy ? a.heavyThr : 0, kHeavySlots, a.heavyMode == 2 ? -1 : max(1, a.ctaSlots / V), a.spreadEmpty, a.extrinsics, a.intrinsics, a.s.cams, V);
   tm->end(st);
   ++launches;
   tm->begin(K_BIN_FILL, st);
