@@ -1,22 +1,24 @@
 // gvv_forward.cu -- forward pass of the rasteriser for sm_100a.
 //
 // Replaces the reference's eight per-batch-element launches (CUDABasedRasterization.cu:449-473)
-// by seven launches that cover ALL batch elements and cameras at once:
+// by six launches that cover ALL batch elements and cameras at once (a seventh, the heavy-tile instance of
+// the raster kernel, when a call has at most two views), chained by programmatic dependent launch:
 //
-//   camera_kernel     per view        E^-1, (K*E)^-1, ray origin            (ref :23-67)
-//   face_normal_kernel per (b, tri)   cross(v1-v0, v2-v0), once per batch element  (ref :122-141)
-//   vertex_kernel     per (b, vertex) /1000 pre-scale, vertex normal via CSR, projection into
-//                                     every camera of b, colour repack       (ref :98-174)
-//   bin_count_kernel  per (view, tri) bbox (ref :184-208) -> tile histogram / big list
-//   bin_scan_kernel   per view        exclusive scan of the tile histogram
-//   bin_fill_kernel   per (view, tri) triangle ids into per-tile bins
-//   raster_kernel     per (view, tile) 64-bit (depth|id) z-tile in shared memory resolved with
-//                                     atomicMin semantics, then resolve + shade + write of all six
-//                                     outputs of the tile (ref :215-408, both raster passes and the
-//                                     28 B/px clear of initializeDevice :74-91 fused away)
+//   face_normal_kernel per (b, tri)    cross(v1-v0, v2-v0), once per batch element          (ref :122-141)
+//   vertex_kernel      per (view, vtx) /1000 pre-scale, vertex normal via CSR (high-valence vertices summed by
+//                                      the whole warp), exact projection, colour repack       (ref :98-174)
+//   bin_count_kernel   per (view, tri) bbox (ref :184-208) -> tile histogram + per-tile range of the triangles'
+//                                      depth-key lower bounds / big-triangle list
+//   bin_scan_kernel    per view        exclusive scan, near/far threshold per tile, raster work list (heaviest
+//                                      tile first), camera records E^-1, (K*E)^-1, ray origin  (ref :23-67)
+//   bin_fill_kernel    per (view, tri) triangle ids into per-tile bins, near ones from the front, far from the back
+//   raster_kernel      per (view, tile) 64-bit (depth|id) z-tile + winner barycentrics in shared memory resolved
+//                                      with atomicMin semantics (one 128-bit CAS), then resolve + shade + write
+//                                      of the outputs of the tile (ref :215-408, both raster passes and the
+//                                      28 B/px clear of initializeDevice :74-91 fused away)
 //
 // No global z-buffer exists: the z-tile lives in shared memory, so HBM sees only the compulsory
-// output stores (24 B/px) plus the (L2-resident) mesh reads.
+// output stores (24 B/px) plus the (L2-resident) mesh reads.  camera_kernel is only used by the normal-map path.
 #include "gvv_internal.h"
 
 namespace gvv {

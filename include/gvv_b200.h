@@ -156,14 +156,19 @@ int64_t gvv_debug_copy(gvv_handle h, int32_t which, void* host_dst, int64_t capa
  * fails the inside test; out_ab: HOST float[n*2] barycentrics (a,b).  Synchronises `stream`. */
 int gvv_debug_eval(gvv_handle h, int32_t n, const int32_t* queries, int32_t* out_key, float* out_ab, void* stream);
 
-/* Runtime knobs: key "tile" (16|32 rasteriser tile edge; default 32); key "cull_margin_milli" (fixed
- * part, in 1/1000 pixel, of the margin of the conservative screen-space pre-test that decides which
- * bbox pixels get the exact test; default 62 (1/16 px); negative = test every bbox pixel exactly, like the
- * reference -- results are identical either way, see tests); key "texture_bilinear" (1: the bilinear
- * texture fetch and the weighted 4-texel texture-gradient scatter the reference has commented out,
- * CUDABasedRasterization.cu:365-372, CUDABasedRasterizationGrad.cu:361-378; default 0 = reference
- * behaviour: nearest texel, unweighted add); key "time_kernels" (1: record
- * a CUDA-event pair around every kernel on the launching stream, 0: off; either resets the log).
+/* Runtime knobs.  Behaviour: "texture_bilinear" (1: the bilinear texture fetch and the weighted 4-texel
+ * texture-gradient scatter the reference has commented out, CUDABasedRasterization.cu:365-372,
+ * CUDABasedRasterizationGrad.cu:361-378; default 0 = reference behaviour: nearest texel, unweighted add).
+ * Scheduling / culling (results are bit-identical for every setting, see tests; defaults = measured best on a
+ * B200): "tile" (16|32 rasteriser tile edge), "cull_margin_milli" (fixed part, in 1/1000 pixel, of the margin of
+ * the conservative screen-space pre-test that decides which bbox pixels get the exact test; default 62 = 1/16 px;
+ * negative = test every bbox pixel exactly, like the reference), "hiz" (two depth passes per tile), "span_z"
+ * (0|1|2 span-level early z: off / both passes / far pass), "batch_div", "cta_threads" (128|256), "interleave",
+ * "ray_cache", "heavy_mode" (0|1|2 1024-thread CTAs for critical-path tiles: never / decided on the GPU for calls
+ * of at most two views / always), "heavy_thr", "heavy_slots", "split_unit", "spread_empty", "resolve_prefetch",
+ * "chain" (programmatic dependent launch of the kernels of a call).  Diagnostics: "time_kernels" (1: record a
+ * CUDA-event pair around every kernel on the launching stream, 0: off; either resets the log), "cta_trace".
+ * The environment variable GVV_OPTIONS="key=value,..." applies knobs to every handle at creation.
  * Returns 0 on success. */
 int gvv_set_option(gvv_handle h, const char* key, int32_t value);
 
