@@ -931,6 +931,7 @@ raster_kernel(const RasterParams p) {
   const float4* vn = p.vnorm4 + (size_t)b * p.N;
   const float4* vc = p.vcol4 + (size_t)b * p.N;
   const bool doShade = (p.shading == GVV_SHADING_SHADED && p.albedo != GVV_ALBEDO_NORMAL) || p.albedo == GVV_ALBEDO_LIGHTING;
+  const bool needNormal = doShade || p.albedo == GVV_ALBEDO_NORMAL;
   if (p.resolvePrefetch) {
     // The resolve loop below walks a thread's pixels one after the other, each with a two-level dependent
     // gather (face -> three vertex normals and colours).  A first sweep pulls those lines into L1 for all of the
@@ -963,12 +964,17 @@ raster_kernel(const RasterParams p) {
       const int4 fc = __ldg(p.faces4 + faceId);
       a = ze.a; bq = ze.b;                               // the winner's barycentrics, stored with its key
       const float c = __fsub_rn(__fsub_rn(1.f, a), bq);  // c = 1 - a - b (RendererUtil.h:125)
-      const F3 rd = ray_of(q);
-      const float4 n0 = __ldg(vn + fc.x), n1 = __ldg(vn + fc.y), n2 = __ldg(vn + fc.z);
-      F3 nr = mk3(interp3(a, bq, c, n0.x, n1.x, n2.x), interp3(a, bq, c, n0.y, n1.y, n2.y), interp3(a, bq, c, n0.z, n1.z, n2.z));
-      const float len = __fsqrt_rn(dot3x(nr, nr));
-      nr = mk3(__fdiv_rn(nr.x, len), __fdiv_rn(nr.y, len), __fdiv_rn(nr.z, len));
-      if (dot3x(nr, rd) > 0.f) nr = mk3(-nr.x, -nr.y, -nr.z);
+      // the pixel normal only reaches the output through the SH shading or the `normal` albedo: shadeless
+      // vertexColor / textured / foregroundMask renders skip the three gathers, the ray, the sqrt and the divides
+      F3 nr = mk3(0.f, 0.f, 1.f);
+      if (needNormal) {
+        const F3 rd = ray_of(q);
+        const float4 n0 = __ldg(vn + fc.x), n1 = __ldg(vn + fc.y), n2 = __ldg(vn + fc.z);
+        nr = mk3(interp3(a, bq, c, n0.x, n1.x, n2.x), interp3(a, bq, c, n0.y, n1.y, n2.y), interp3(a, bq, c, n0.z, n1.z, n2.z));
+        const float len = __fsqrt_rn(dot3x(nr, nr));
+        nr = mk3(__fdiv_rn(nr.x, len), __fdiv_rn(nr.y, len), __fdiv_rn(nr.z, len));
+        if (dot3x(nr, rd) > 0.f) nr = mk3(-nr.x, -nr.y, -nr.z);
+      }
       if (p.albedo == GVV_ALBEDO_TEXTURED) {
         const float* tc = p.texcoords + (size_t)faceId * 6;
         const float u = interp3(a, bq, c, __ldg(tc + 0), __ldg(tc + 2), __ldg(tc + 4));
