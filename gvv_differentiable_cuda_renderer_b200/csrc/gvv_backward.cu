@@ -150,6 +150,10 @@ __device__ __forceinline__ V3 ld4(const float4* __restrict__ p, size_t i) { cons
 // their segments without any block barrier, and the SH gradient is reduced once per tile.
 constexpr int kSlabs = 4;
 
+// SHADED is a template parameter: the shaded instance is the full chain; the shadeless one drops, at compile time,
+// everything its gradients do not depend on (SH basis and light, the albedo VALUE and its texel / colour gathers,
+// the shading-normal position term and its buffers), which the register allocator could not do behind a runtime flag.
+template <bool SHADED>
 __global__ void __launch_bounds__(256, 4)
 pixel_grad_kernel(const PixelParams p) {
   chain_wait(); chain_trigger();
@@ -169,7 +173,7 @@ pixel_grad_kernel(const PixelParams p) {
     const int f = (x < p.W && ys < p.H) ? __ldg(p.face + viewBase + (size_t)ys * p.W + x) : -1;
     any = any || f >= 0;
   }
-  const bool shaded = p.shading == GVV_SHADING_SHADED;
+  constexpr bool shaded = SHADED;
 
   // camera + SH staging overlaps the latency of the face loads; ONE barrier publishes both and
   // tells whether anything is visible in this 32x32 tile
@@ -207,13 +211,16 @@ pixel_grad_kernel(const PixelParams p) {
       mine[(kVals + kShRows + 2) * kRow] = __int_as_float(fc.z);
       const float4* pos = p.pos4 + (size_t)b * p.N;
       const float4* nor = p.nor4 + (size_t)view * p.N;
-      const V3 p0 = ld4(pos, fc.x), p1 = ld4(pos, fc.y), p2 = ld4(pos, fc.z);
-      const V3 n0 = ld4(nor, fc.x), n1 = ld4(nor, fc.y), n2 = ld4(nor, fc.z);
-      const V3 nUn = bc[0] * n0 + bc[1] * n1 + bc[2] * n2;
+      // (conditions that start with `shaded ||` are compile-time true in the shaded instance)
+      V3 p0 = v3(0.f, 0.f, 0.f), p1 = p0, p2 = p0, n0 = p0, n1 = p0, n2 = p0;
+      if (shaded || p.target_grad) { p0 = ld4(pos, fc.x); p1 = ld4(pos, fc.y); p2 = ld4(pos, fc.z); }   // positions: shading-normal and model-to-data terms
+      const bool needNormal = shaded || p.albedo == GVV_ALBEDO_TEXTURED;                                   // pixel normal: shading, and the flipped-normal rule of the texture gradient
+      if (needNormal) { n0 = ld4(nor, fc.x); n1 = ld4(nor, fc.y); n2 = ld4(nor, fc.z); }
+      const V3 nUn = needNormal ? bc[0] * n0 + bc[1] * n1 + bc[2] * n2 : v3(0.f, 0.f, 1.f);
       const float len2 = dot(nUn, nUn);
       const float ilen = rsqrtf(len2);
       V3 n = ilen * nUn;
-      const bool flipped = dot(n, d) > 0.f;
+      const bool flipped = needNormal && dot(n, d) > 0.f;
       if (flipped) n = v3(-n.x, -n.y, -n.z);
 
       // SH basis (getIllum / getJLiGm, RendererUtil.h:179-214,351-364)
@@ -233,10 +240,12 @@ pixel_grad_kernel(const PixelParams p) {
       // ---- albedo (:242-319) and its gradients (:327-395) ----
       float alb[3] = {0.f, 0.f, 0.f};
       if (p.albedo == GVV_ALBEDO_VERTEX_COLOR) {
-        const float4* col = p.col4 + (size_t)b * p.N;
-        const V3 c0 = ld4(col, fc.x), c1 = ld4(col, fc.y), c2 = ld4(col, fc.z);
-        const V3 al = bc[0] * c0 + bc[1] * c1 + bc[2] * c2;
-        alb[0] = al.x; alb[1] = al.y; alb[2] = al.z;
+        if (shaded) {      // the albedo VALUE only feeds the SH and shading-normal gradients
+          const float4* col = p.col4 + (size_t)b * p.N;
+          const V3 c0 = ld4(col, fc.x), c1 = ld4(col, fc.y), c2 = ld4(col, fc.z);
+          const V3 al = bc[0] * c0 + bc[1] * c1 + bc[2] * c2;
+          alb[0] = al.x; alb[1] = al.y; alb[2] = al.z;
+        }
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -251,7 +260,8 @@ pixel_grad_kernel(const PixelParams p) {
         const float LV = (float)(int)(v - 0.5f) + 0.5f, HV = (float)(int)(v - 0.5f) + 1.5f;
         const float* tex = p.texture + (size_t)b * p.texH * p.texW * 3;
         const int lu = (int)LU, hu = min((int)HU, p.texW - 1), lv = (int)LV, hv = min((int)HV, p.texH - 1);   // hu, hv only clamp for 1-texel-wide textures
-        // bilinear mix exactly as written in :311-312 (the forward uses the nearest texel)
+        // bilinear mix exactly as written in :311-312 (the forward uses the nearest texel); only shaded modes use the value
+        if (shaded)
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
           const float cLULV = __ldg(tex + 3 * ((size_t)p.texW * lv + lu) + ch), cLUHV = __ldg(tex + 3 * ((size_t)p.texW * hv + lu) + ch);
@@ -537,8 +547,13 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   tm->begin(K_PIXEL_GRAD, st);
   constexpr int kPixelSmem = 8 * kWarpBufFloats * (int)sizeof(float);
   static bool pgAttr = false;
-  if (!pgAttr) { cudaFuncSetAttribute(pixel_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPixelSmem); pgAttr = true; }
-  launch_chained(a.chain, pixel_grad_kernel, dim3((a.W + 31) / 32, (a.H + 31) / 32, V), dim3(256), kPixelSmem, st, p);
+  if (!pgAttr) {
+    cudaFuncSetAttribute(pixel_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPixelSmem);
+    cudaFuncSetAttribute(pixel_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPixelSmem);
+    pgAttr = true;
+  }
+  if (a.shading == GVV_SHADING_SHADED) launch_chained(a.chain, pixel_grad_kernel<true>, dim3((a.W + 31) / 32, (a.H + 31) / 32, V), dim3(256), kPixelSmem, st, p);
+  else launch_chained(a.chain, pixel_grad_kernel<false>, dim3((a.W + 31) / 32, (a.H + 31) / 32, V), dim3(256), kPixelSmem, st, p);
   tm->end(st);
   ++launches;
   if (a.shading == GVV_SHADING_SHADED) {
