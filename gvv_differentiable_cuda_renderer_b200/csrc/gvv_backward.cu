@@ -153,7 +153,7 @@ constexpr int kSlabs = 4;
 // SHADED is a template parameter: the shaded instance is the full chain; the shadeless one drops, at compile time,
 // everything its gradients do not depend on (SH basis and light, the albedo VALUE and its texel / colour gathers,
 // the shading-normal position term and its buffers), which the register allocator could not do behind a runtime flag.
-template <bool SHADED>
+template <bool SHADED, int ALBEDO>
 __global__ void __launch_bounds__(256, 4)
 pixel_grad_kernel(const PixelParams p) {
   chain_wait(); chain_trigger();
@@ -174,6 +174,7 @@ pixel_grad_kernel(const PixelParams p) {
     any = any || f >= 0;
   }
   constexpr bool shaded = SHADED;
+  constexpr int albedo = ALBEDO;       // vertexColor | textured | foregroundMask (the other modes have no gradient)
 
   // camera + SH staging overlaps the latency of the face loads; ONE barrier publishes both and
   // tells whether anything is visible in this 32x32 tile
@@ -214,7 +215,7 @@ pixel_grad_kernel(const PixelParams p) {
       // (conditions that start with `shaded ||` are compile-time true in the shaded instance)
       V3 p0 = v3(0.f, 0.f, 0.f), p1 = p0, p2 = p0, n0 = p0, n1 = p0, n2 = p0;
       if (shaded || p.target_grad) { p0 = ld4(pos, fc.x); p1 = ld4(pos, fc.y); p2 = ld4(pos, fc.z); }   // positions: shading-normal and model-to-data terms
-      const bool needNormal = shaded || p.albedo == GVV_ALBEDO_TEXTURED;                                   // pixel normal: shading, and the flipped-normal rule of the texture gradient
+      const bool needNormal = shaded || albedo == GVV_ALBEDO_TEXTURED;                                   // pixel normal: shading, and the flipped-normal rule of the texture gradient
       if (needNormal) { n0 = ld4(nor, fc.x); n1 = ld4(nor, fc.y); n2 = ld4(nor, fc.z); }
       const V3 nUn = needNormal ? bc[0] * n0 + bc[1] * n1 + bc[2] * n2 : v3(0.f, 0.f, 1.f);
       const float len2 = dot(nUn, nUn);
@@ -239,7 +240,7 @@ pixel_grad_kernel(const PixelParams p) {
 
       // ---- albedo (:242-319) and its gradients (:327-395) ----
       float alb[3] = {0.f, 0.f, 0.f};
-      if (p.albedo == GVV_ALBEDO_VERTEX_COLOR) {
+      if (albedo == GVV_ALBEDO_VERTEX_COLOR) {
         if (shaded) {      // the albedo VALUE only feeds the SH and shading-normal gradients
           const float4* col = p.col4 + (size_t)b * p.N;
           const V3 c0 = ld4(col, fc.x), c1 = ld4(col, fc.y), c2 = ld4(col, fc.z);
@@ -250,7 +251,7 @@ pixel_grad_kernel(const PixelParams p) {
         for (int i = 0; i < 3; ++i)
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) mine[(i * 3 + ch) * kRow] = gl[ch] * bc[i];
-      } else if (p.albedo == GVV_ALBEDO_TEXTURED) {
+      } else if (albedo == GVV_ALBEDO_TEXTURED) {
         const float* tc = p.texcoords + (size_t)face * 6;
         float u = (__ldg(tc + 0) * bc[0] + __ldg(tc + 2) * bc[1] + __ldg(tc + 4) * bc[2]) * p.texW;
         float v = ((1.f - __ldg(tc + 1)) * bc[0] + (1.f - __ldg(tc + 3)) * bc[1] + (1.f - __ldg(tc + 5)) * bc[2]) * p.texH;
@@ -381,7 +382,7 @@ pixel_grad_kernel(const PixelParams p) {
     const unsigned endm = cv & ~cont;
     __syncwarp();
     const int arr = lane / 9, vi = (lane % 9) / 3, comp = lane % 3;
-    const bool active = lane < kVals && ((arr == 0 && p.albedo == GVV_ALBEDO_VERTEX_COLOR) ||
+    const bool active = lane < kVals && ((arr == 0 && albedo == GVV_ALBEDO_VERTEX_COLOR) ||
                                          (arr == 1 && (shaded || p.target_grad)) || (arr == 2 && shaded));
     float* base = arr == 0 ? p.vcol_grad : (arr == 1 ? p.vpos_grad : p.gnorm);
     const int vstride = arr == 2 ? 4 : 3;          // gnorm is float4-strided for aligned gathers in normal_term_kernel
@@ -546,14 +547,15 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   p.albedo = a.albedo; p.shading = a.shading; p.imgFilter = a.imgFilter; p.texBilinear = a.texBilinear; p.invC = 1.f / (float)a.C;
   tm->begin(K_PIXEL_GRAD, st);
   constexpr int kPixelSmem = 8 * kWarpBufFloats * (int)sizeof(float);
-  static bool pgAttr = false;
-  if (!pgAttr) {
-    cudaFuncSetAttribute(pixel_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPixelSmem);
-    cudaFuncSetAttribute(pixel_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPixelSmem);
-    pgAttr = true;
-  }
-  if (a.shading == GVV_SHADING_SHADED) launch_chained(a.chain, pixel_grad_kernel<true>, dim3((a.W + 31) / 32, (a.H + 31) / 32, V), dim3(256), kPixelSmem, st, p);
-  else launch_chained(a.chain, pixel_grad_kernel<false>, dim3((a.W + 31) / 32, (a.H + 31) / 32, V), dim3(256), kPixelSmem, st, p);
+  const dim3 pgGrid((a.W + 31) / 32, (a.H + 31) / 32, V);
+#define GVV_PG(S, A) do { static bool attr = false; \
+    if (!attr) { cudaFuncSetAttribute(pixel_grad_kernel<S, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPixelSmem); attr = true; } \
+    launch_chained(a.chain, pixel_grad_kernel<S, A>, pgGrid, dim3(256), kPixelSmem, st, p); } while (0)
+  const bool sh = a.shading == GVV_SHADING_SHADED;
+  if (a.albedo == GVV_ALBEDO_VERTEX_COLOR) { if (sh) GVV_PG(true, GVV_ALBEDO_VERTEX_COLOR); else GVV_PG(false, GVV_ALBEDO_VERTEX_COLOR); }
+  else if (a.albedo == GVV_ALBEDO_TEXTURED) { if (sh) GVV_PG(true, GVV_ALBEDO_TEXTURED); else GVV_PG(false, GVV_ALBEDO_TEXTURED); }
+  else { if (sh) GVV_PG(true, GVV_ALBEDO_FOREGROUND_MASK); else GVV_PG(false, GVV_ALBEDO_FOREGROUND_MASK); }   // foregroundMask (and any mode without an albedo gradient)
+#undef GVV_PG
   tm->end(st);
   ++launches;
   if (a.shading == GVV_SHADING_SHADED) {
