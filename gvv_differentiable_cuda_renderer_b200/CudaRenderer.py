@@ -98,6 +98,8 @@ def _as_cuda(x, device, name):
     if x is None:
         raise _native.GvvError(f"{name} is required")
     if isinstance(x, torch.Tensor):
+        if x.dtype is torch.float32 and x.device == device:      # the common case costs no dispatcher call
+            return x
         return x.to(device=device, dtype=torch.float32)
     return torch.as_tensor(np.asarray(x, dtype=np.float32), device=device)
 

@@ -109,17 +109,35 @@ def _check(rc, what):
 
 
 def _ptr(t):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    return None if t is None else t.data_ptr()      # ctypes converts the int through argtypes = c_void_p
 
 
 def _f32(t, name, device):
     if t is None:
         return None
+    if t.dtype is torch.float32 and t.device == device and t.is_contiguous():   # fast path: nothing to do
+        return t
     if t.device != device:
         raise GvvError(f"{name} is on {t.device}, the renderer lives on {device}")
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def _device_ctx(dev):
+    """torch.cuda.device(dev) only when dev is not already current (the context manager costs ~10 us per call)."""
+    return _NULL if torch.cuda.current_device() == (dev.index or 0) else torch.cuda.device(dev)
 
 
 class NativeRenderer:
@@ -172,7 +190,7 @@ class NativeRenderer:
         return int(lib().gvv_launch_count(self._h))
 
     def _stream(self):
-        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return torch.cuda.current_stream(self.device).cuda_stream
 
     def forward(self, vertex_pos, vertex_color, texture, sh_coeff, target_image, extrinsics, intrinsics):
         dev = self.device
@@ -190,7 +208,7 @@ class NativeRenderer:
            extrinsics.numel() != B * C * 12 or intrinsics.numel() != B * C * 9:
             raise GvvError("input tensor sizes do not match batch/cameras/vertices")
         o = dict(device=dev, dtype=torch.float32)
-        with torch.cuda.device(dev):
+        with _device_ctx(dev):
             bary = torch.empty((B, C, H, W, 2), **o)
             face = torch.empty((B, C, H, W), device=dev, dtype=torch.int32)
             render = torch.empty((B, C, H, W, 3), **o)
@@ -226,7 +244,7 @@ class NativeRenderer:
         extrinsics = _f32(extrinsics, "extrinsics", dev)
         intrinsics = _f32(intrinsics, "intrinsics", dev)
         o = dict(device=dev, dtype=torch.float32)
-        with torch.cuda.device(dev):
+        with _device_ctx(dev):
             pre = tuple(out) if out is not None else (None, None, None, None)
             shapes = ((B, N, 3), (B, N, 3), (B, texH, texW, 3), (B, C, 27))
             outs = []
