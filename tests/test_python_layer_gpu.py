@@ -139,3 +139,40 @@ def test_texture_fitting_with_the_bilinear_variant_and_smoothing():
     # the default layer on the same attributes is a different handle (nearest texel): different image
     near = layer(sc, t, "textured", "shadeless").getRenderBufferTF()
     assert not torch.equal(near, target)
+
+
+def test_layer_step_is_cuda_graph_capturable_through_autograd():
+    """A whole fit step through the public layer -- CudaRendererGpu(...), loss, autograd -- captured with
+    torch.cuda.graph and replayed on new input values reproduces the eager loss and gradients (bench.py's e2e leg)."""
+    sc, t = scene(kind="sphere", rings=20, segments=24, cameras=2, width=128, height=96, tex=16)
+    dev = t["vertex_pos"].device
+    g_img = torch.randn((1, 2, 96, 128, 3), generator=torch.Generator().manual_seed(0)).to(dev)
+    static = {k: t[k].clone() for k in ("vertex_pos", "vertex_color", "sh_coeff")}
+
+    def step(d):
+        leaves = {k: d[k].detach().requires_grad_(True) for k in d}
+        r = layer(sc, t, "vertexColor", "shaded", vertexPos_input=leaves["vertex_pos"], vertexColor_input=leaves["vertex_color"],
+                  shCoeff_input=leaves["sh_coeff"])
+        loss = (r.getRenderBufferTF() * g_img).sum()
+        return loss, torch.autograd.grad(loss, list(leaves.values()))
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step(static)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss_s, grads_s = step(static)
+    for trial in range(2):
+        static["vertex_color"].copy_(torch.rand_like(static["vertex_color"]))       # new values in the static inputs
+        static["sh_coeff"].mul_(1.0 + 0.1 * trial)
+        graph.replay()
+        torch.cuda.synchronize()
+        loss_e, grads_e = step({k: v.clone() for k, v in static.items()})
+        assert abs(float(loss_s) - float(loss_e)) <= 1e-4 * max(1.0, abs(float(loss_e)))
+        for a, b in zip(grads_s, grads_e):
+            assert float((a - b).norm()) <= 1e-4 * float(b.norm()) + 1e-6
+    del graph
