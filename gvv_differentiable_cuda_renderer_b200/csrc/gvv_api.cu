@@ -232,6 +232,7 @@ extern "C" int gvv_set_option(gvv_handle h, const char* key, int32_t value) {
   if (!strcmp(key, "heavy_slots")) { if (value < 1 || value > 1024) return fail(GVV_EINVAL, "heavy_slots must be in [1,1024]"); h->heavySlots = value; return GVV_OK; }
   if (!strcmp(key, "heavy_thr")) { if (value < 0) return fail(GVV_EINVAL, "heavy_thr must be >= 0"); h->heavyThr = value; return GVV_OK; }
   if (!strcmp(key, "split_unit")) { if (value < 0) return fail(GVV_EINVAL, "split_unit must be >= 0"); h->splitUnit = value; return GVV_OK; }
+  if (!strcmp(key, "hiz_min")) { if (value < 0) return fail(GVV_EINVAL, "hiz_min must be >= 0"); h->hizMin = value; return GVV_OK; }
   if (!strcmp(key, "hiz")) { h->hiz = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "interleave")) { h->interleave = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "ray_cache")) { h->rayCache = value ? 1 : 0; return GVV_OK; }
@@ -275,7 +276,7 @@ extern "C" int gvv_forward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
   FwdArgs a;
   a.B = B; a.C = h->C; a.N = h->N; a.F = h->F; a.W = h->W; a.H = h->H; a.texH = texH; a.texW = texW;
   a.albedo = h->albedo; a.shading = h->shading;
-  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin; a.rayCache = h->rayCache; a.batchDiv = h->batchDiv; a.ctaThreads = h->ctaThreads; a.interleave = h->interleave; a.hiz = h->hiz; a.spanZ = h->spanZ; a.splitUnit = h->splitUnit; a.heavyThr = h->heavyThr; a.heavySlots = h->heavySlots; a.heavyMode = h->heavyMode; a.ctaSlots = h->ctaSlots; a.spreadEmpty = h->spreadEmpty; a.texBilinear = h->texBilinear; a.resolvePrefetch = h->resolvePrefetch; a.chain = h->chain && !h->timer.enabled;   // per-kernel timing wants plain stream order
+  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin; a.rayCache = h->rayCache; a.batchDiv = h->batchDiv; a.ctaThreads = h->ctaThreads; a.interleave = h->interleave; a.hiz = h->hiz; a.hizMin = h->hizMin; a.spanZ = h->spanZ; a.splitUnit = h->splitUnit; a.heavyThr = h->heavyThr; a.heavySlots = h->heavySlots; a.heavyMode = h->heavyMode; a.ctaSlots = h->ctaSlots; a.spreadEmpty = h->spreadEmpty; a.texBilinear = h->texBilinear; a.resolvePrefetch = h->resolvePrefetch; a.chain = h->chain && !h->timer.enabled;   // per-kernel timing wants plain stream order
   a.vertex_pos = vertex_pos; a.vertex_color = vertex_color; a.texture = texture; a.sh_coeff = sh_coeff;
   a.extrinsics = extrinsics; a.intrinsics = intrinsics; a.texcoords = h->texcoords;
   a.faces4 = h->faces4; a.vfOffsets = h->vfOffsets; a.vfList = h->vfList;

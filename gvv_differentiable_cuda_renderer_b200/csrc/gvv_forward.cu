@@ -523,7 +523,7 @@ struct RasterParams {
   const float* texture; const float* texcoords; const float* sh_coeff;
   float* bary; int32_t* face; float* render;
   unsigned long long* ctaTrace;
-  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, spanZ, role, pdl, grid2d, texBilinear, resolvePrefetch;
+  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, hizMin, spanZ, role, pdl, grid2d, texBilinear, resolvePrefetch;
   float cullMargin;
 };
 
@@ -739,7 +739,7 @@ raster_kernel(const RasterParams p) {
   // ever decrease, so such a triangle can win no pixel: the result is bit-identical (hiz = 0 and short bins
   // rasterise everything in one pass). ----
   const int nNear = p.tileCursor[tidx];
-  const bool twoPass = p.hiz && cntAll >= 64 && nNear < cntSmall;
+  const bool twoPass = p.hiz && cntAll >= p.hizMin && nNear < cntSmall;
   for (int pass = 0; pass < 2; ++pass) {
   unsigned zmaxBits = 0xffffffffu;                    // pass 1: farthest current winner of the tile (0xffffffff if a pixel is still empty)
   if (pass == 1) {
@@ -1140,7 +1140,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   p.texture = a.texture; p.texcoords = a.texcoords; p.sh_coeff = a.sh_coeff;
   p.bary = a.bary; p.face = a.face; p.render = a.render; p.ctaTrace = a.s.ctaTrace;
   p.C = a.C; p.N = a.N; p.F = a.F; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
-  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv; p.interleave = a.interleave; p.hiz = a.hiz; p.spanZ = a.spanZ; p.texBilinear = a.texBilinear; p.resolvePrefetch = a.resolvePrefetch;
+  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv; p.interleave = a.interleave; p.hiz = a.hiz; p.hizMin = a.hizMin; p.spanZ = a.spanZ; p.texBilinear = a.texBilinear; p.resolvePrefetch = a.resolvePrefetch;
   p.grid2d = nItems <= 65535 ? 1 : 0;
   const dim3 gridT = p.grid2d ? dim3((unsigned)V, (unsigned)nItems) : dim3((unsigned)nItems * (unsigned)V);
   tm->begin(K_RASTER, st);

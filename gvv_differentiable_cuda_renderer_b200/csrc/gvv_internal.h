@@ -76,6 +76,7 @@ struct gvv_renderer {
   int splitUnit = 0;          // raster: a bin of >= splitUnit (2x, 4x) triangles is cut into 2 (4, 8) strips with a CTA each; 0 = never (measured slower: every strip re-scans the bin)
   int ctaTrace = 0;           // debug: record per-CTA start/end times of the raster kernel
   int spanZ = 2;              // raster: trim every row span to the pixels whose current winner the triangle could still beat (1 = both passes, 2 = far pass only)
+  int hizMin = 64;            // raster: bins shorter than this are rasterised in one pass
   int hiz = 1;                // raster: two-pass hierarchical z (skips triangles behind the whole tile)
   int interleave = 1;         // raster: batch j takes bin entries j, j+nBatches, ... instead of a contiguous chunk
   int ctaThreads = 256;       // raster: threads per tile CTA (256 | 128)
@@ -98,7 +99,7 @@ namespace gvv {
 
 struct FwdArgs {
   int B, C, N, F, W, H, texH, texW, albedo, shading;
-  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, spanZ, splitUnit, heavyThr, heavyMode, heavySlots, ctaSlots, spreadEmpty, texBilinear, resolvePrefetch, chain;
+  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, hizMin, spanZ, splitUnit, heavyThr, heavyMode, heavySlots, ctaSlots, spreadEmpty, texBilinear, resolvePrefetch, chain;
   float cullMargin;
   const float *vertex_pos, *vertex_color, *texture, *sh_coeff, *extrinsics, *intrinsics;
   const float* texcoords;

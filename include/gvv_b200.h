@@ -162,7 +162,7 @@ int gvv_debug_eval(gvv_handle h, int32_t n, const int32_t* queries, int32_t* out
  * Scheduling / culling (results are bit-identical for every setting, see tests; defaults = measured best on a
  * B200): "tile" (16|32 rasteriser tile edge), "cull_margin_milli" (fixed part, in 1/1000 pixel, of the margin of
  * the conservative screen-space pre-test that decides which bbox pixels get the exact test; default 62 = 1/16 px;
- * negative = test every bbox pixel exactly, like the reference), "hiz" (two depth passes per tile), "span_z"
+ * negative = test every bbox pixel exactly, like the reference), "hiz" (two depth passes per tile), "hiz_min" (bins shorter than this: one pass), "span_z"
  * (0|1|2 span-level early z: off / both passes / far pass), "batch_div", "cta_threads" (128|256), "interleave",
  * "ray_cache", "heavy_mode" (0|1|2 1024-thread CTAs for critical-path tiles: never / decided on the GPU for calls
  * of at most two views / always), "heavy_thr", "heavy_slots", "split_unit", "spread_empty", "resolve_prefetch",
