@@ -1089,6 +1089,8 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const dim3 gridF((a.F + 256 * kBinFacesPerThread - 1) / (256 * kBinFacesPerThread), V);
   tm->begin(K_BIN_COUNT, st);
   if (a.nT <= kSmemHistTiles) {
+    static bool countAttr = false;
+    if (!countAttr) { cudaFuncSetAttribute(bin_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kSmemHistTiles * (int)sizeof(int)); countAttr = true; }
     launch_chained(a.chain, bin_count_kernel<true>, gridF, dim3(256), 3 * a.nT * sizeof(int), st, a.faces4, a.s.proj, a.s.tileCount, a.s.tileMinK, a.s.tileMaxK,
                    a.s.bigCount, a.s.bigList, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
   } else {

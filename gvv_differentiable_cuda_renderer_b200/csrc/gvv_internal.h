@@ -11,7 +11,7 @@ namespace gvv {
 // which every tile of that view scans; everything else is appended to per-tile bins.  This bounds
 // the bin pool by F*kMaxSmallTiles entries per view without ever reading a count back to the host.
 constexpr int kMaxSmallTiles = 16;
-constexpr int kSmemHistTiles = 4096;   // largest tile grid handled with a shared-memory histogram
+constexpr int kSmemHistTiles = 12288;  // largest tile grid handled with shared-memory histograms (3840x2160 at 32x32 = 8160 tiles; bin_fill needs 16 B per tile: 192 KB)
 
 struct Scratch {
   int capViews = 0, capBatch = 0;
