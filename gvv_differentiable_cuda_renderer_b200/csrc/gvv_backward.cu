@@ -548,8 +548,8 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   tm->begin(K_PIXEL_GRAD, st);
   constexpr int kPixelSmem = 8 * kWarpBufFloats * (int)sizeof(float);
   const dim3 pgGrid((a.W + 31) / 32, (a.H + 31) / 32, V);
-#define GVV_PG(S, A) do { static bool attr = false; \
-    if (!attr) { cudaFuncSetAttribute(pixel_grad_kernel<S, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPixelSmem); attr = true; } \
+#define GVV_PG(S, A) do { static unsigned long long attr = 0; \
+    if (first_use_on_device(&attr)) cudaFuncSetAttribute(pixel_grad_kernel<S, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPixelSmem); \
     launch_chained(a.chain, pixel_grad_kernel<S, A>, pgGrid, dim3(256), kPixelSmem, st, p); } while (0)
   const bool sh = a.shading == GVV_SHADING_SHADED;
   if (a.albedo == GVV_ALBEDO_VERTEX_COLOR) { if (sh) GVV_PG(true, GVV_ALBEDO_VERTEX_COLOR); else GVV_PG(false, GVV_ALBEDO_VERTEX_COLOR); }

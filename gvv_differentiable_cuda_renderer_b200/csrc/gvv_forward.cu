@@ -1089,8 +1089,8 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const dim3 gridF((a.F + 256 * kBinFacesPerThread - 1) / (256 * kBinFacesPerThread), V);
   tm->begin(K_BIN_COUNT, st);
   if (a.nT <= kSmemHistTiles) {
-    static bool countAttr = false;
-    if (!countAttr) { cudaFuncSetAttribute(bin_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kSmemHistTiles * (int)sizeof(int)); countAttr = true; }
+    static unsigned long long countAttr = 0;
+    if (first_use_on_device(&countAttr)) cudaFuncSetAttribute(bin_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kSmemHistTiles * (int)sizeof(int));
     launch_chained(a.chain, bin_count_kernel<true>, gridF, dim3(256), 3 * a.nT * sizeof(int), st, a.faces4, a.s.proj, a.s.tileCount, a.s.tileMinK, a.s.tileMaxK,
                    a.s.bigCount, a.s.bigList, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
   } else {
@@ -1115,8 +1115,8 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const bool fewViews = (smCount / 4) / max(V, 1) >= 16 || a.heavyMode == 2;
   const bool useHeavy = a.heavyMode > 0 && a.heavyThr > 0 && a.tile == 32 && !a.rayCache && a.ctaThreads == 256 && fewViews;
   const int maxLog = a.splitUnit > 0 ? (a.tile == 32 ? 3 : 2) : 0;
-  static bool scanAttr = false;
-  if (!scanAttr) { cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); scanAttr = true; }
+  static unsigned long long scanAttr = 0;
+  if (first_use_on_device(&scanAttr)) cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   if ((size_t)a.nT * sizeof(int) > 160 * 1024) return -1;   // 40960 tiles = e.g. 6400 x 6400 pixels at 32 x 32; larger grids are not supported
   launch_chained(a.chain, bin_scan_kernel, dim3(V + (V + 1023) / 1024), dim3(1024), a.nT * sizeof(int), st, a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.s.tileMinK, a.s.tileMaxK, a.s.tileThr,
                  a.nT, a.tilesX, nItems, a.splitUnit > 0 ? a.splitUnit : 1, maxLog,
@@ -1125,8 +1125,8 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   ++launches;
   tm->begin(K_BIN_FILL, st);
   if (a.nT <= kSmemHistTiles) {
-    static bool fillAttr = false;
-    if (!fillAttr) { cudaFuncSetAttribute(bin_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSmemHistTiles * (int)sizeof(int)); fillAttr = true; }
+    static unsigned long long fillAttr = 0;
+    if (first_use_on_device(&fillAttr)) cudaFuncSetAttribute(bin_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSmemHistTiles * (int)sizeof(int));
     launch_chained(a.chain, bin_fill_kernel<true>, gridF, dim3(256), 4 * a.nT * sizeof(int), st, a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCount, a.s.tileThr,
                    a.s.tileCursor, a.s.tileCursorFar, a.s.bins, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
   } else {
@@ -1146,13 +1146,12 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   p.grid2d = nItems <= 65535 ? 1 : 0;
   const dim3 gridT = p.grid2d ? dim3((unsigned)V, (unsigned)nItems) : dim3((unsigned)nItems * (unsigned)V);
   tm->begin(K_RASTER, st);
-  static bool attrSet = false;
-  if (!attrSet) {   // > 48 KB of dynamic shared memory needs the opt-in (once per process and device function)
+  static unsigned long long attrSet = 0;
+  if (first_use_on_device(&attrSet)) {   // > 48 KB of dynamic shared memory needs the opt-in (once per device and device function)
 #define GVV_RASTER_ATTR(TS, RC, NTH) cudaFuncSetAttribute(raster_kernel<TS, RC, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<TS, RC, NTH>())
     GVV_RASTER_ATTR(16, true, 256); GVV_RASTER_ATTR(32, true, 256); GVV_RASTER_ATTR(16, false, 256); GVV_RASTER_ATTR(32, false, 256);
     GVV_RASTER_ATTR(16, false, 128); GVV_RASTER_ATTR(32, false, 128); GVV_RASTER_ATTR(32, false, 1024);
 #undef GVV_RASTER_ATTR
-    attrSet = true;
   }
   // The heavy launch goes FIRST, so that its one-SM CTAs are placed while the SMs are empty (behind the small CTAs
   // they would starve until the very end -- measured).  The 256-thread launch follows on the SAME stream as a

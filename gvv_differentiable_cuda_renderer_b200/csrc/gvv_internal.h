@@ -140,6 +140,17 @@ inline cudaError_t launch_chained(bool chained, void (*kernel)(KArgs...), dim3 g
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncSetAttribute is per DEVICE: the opt-in for more than 48 KB of dynamic shared memory is repeated on every
+// device a handle lives on (one flag word per kernel, one bit per device; a process normally drives one GPU).
+inline bool first_use_on_device(unsigned long long* flags) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*flags & bit) return false;
+  *flags |= bit;
+  return true;
+}
+
 // Each returns the number of kernels launched, or -1 after a launch error.
 int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm);
 int launch_normal_map(const FwdArgs& a, const float4* texelTable, float* normal_map, cudaStream_t st);

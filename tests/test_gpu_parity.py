@@ -483,3 +483,23 @@ def test_every_tuning_knob_keeps_the_bits(opts):
         assert torch.equal(r1.view(torch.int32), r0.view(torch.int32))
         assert torch.equal(v1, v0)
     base.close(); r.close()
+
+
+@pytest.mark.skipif(torch.cuda.is_available() and torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """Handles on two devices of the same process (the shared-memory opt-ins are per device): same bits on both."""
+    sc = synthetic.make_scene(kind="sphere", rings=40, segments=48, cameras=2, width=160, height=128, tex=16, seed=12)
+    outs = []
+    for d in (0, 1):
+        dv = torch.device("cuda", d)
+        ins = [torch.as_tensor(np.ascontiguousarray(sc[k]), device=dv) for k in INPUT_KEYS]
+        r = _native.NativeRenderer(sc["faces"], sc["texcoords"], sc["num_vertices"], sc["num_cameras"], sc["width"], sc["height"],
+                                   "vertexColor", "shaded", 1, 1, False, dv)
+        with torch.cuda.device(dv):
+            bary, face, render, vn, _, _ = r.forward(*ins)
+            g = r.backward(torch.ones_like(render), None, ins[0], ins[1], ins[2], ins[3], ins[4], vn, bary, face, ins[5], ins[6])
+            torch.cuda.synchronize(dv)
+        outs.append((face.cpu(), render.cpu(), g[1].cpu()))
+        r.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert float((outs[0][2] - outs[1][2]).abs().max()) <= 1e-4 * float(outs[0][2].abs().max())
