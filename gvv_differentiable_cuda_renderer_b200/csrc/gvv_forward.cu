@@ -1104,12 +1104,12 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   // Heavy bins (>= heavyThr triangles among the kHeavySlots heaviest items of a view) get a 1024-thread CTA, i.e.
   // a whole SM, from a second launch: a 256-thread CTA shares its SM with three others and would make the
   // tile the critical path of the launch (1M triangles at 3840x2160, one view: 1.53 ms -> 0.59 ms).  Which bins
-  // qualify is decided on the GPU (bin_scan_kernel).  A CTA that needs a whole SM must find one empty, and a
-  // launch of one such CTA per SM -- even one whose CTAs all leave at once -- slowed the end-to-end step through
-  // the Python layer by 10 % (a quarter of the SMs: nothing, measured).  So the heavy launch holds at most SMs/4
-  // CTAs, split evenly over the views, and is dropped when that leaves fewer than 16 per view (more than two views
-  // on a B200): a single tile can only be the critical path of a launch that has very few views -- the work of
-  // the other tiles grows with the number of views, the longest tile does not.  heavy_mode 2 skips this gate.
+  // qualify is decided on the GPU (bin_scan_kernel).  A CTA that needs a whole SM must find one empty and its
+  // per-triangle cost is ~1.5x that of a 256-thread CTA (32 warps on one z-tile), so with many views the launch
+  // only costs (8 views, 70k triangles: 0.298 -> 0.307 ms).  The heavy launch therefore holds at most SMs/4 CTAs,
+  // split evenly over the views, and is dropped when that leaves fewer than 16 per view (more than two views on
+  // a B200): a single tile can only be the critical path of a launch that has very few views -- the work of the
+  // other tiles grows with the number of views, the longest tile does not.  heavy_mode 2 skips this gate.
   const int smCount = max(1, a.ctaSlots / 4);
   const int kHeavySlots = min(min(nItems, a.heavySlots), max(1, (smCount / 4) / max(V, 1)));
   const bool fewViews = (smCount / 4) / max(V, 1) >= 16 || a.heavyMode == 2;
@@ -1158,8 +1158,8 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   // programmatic dependent launch: the heavy CTAs signal griddepcontrol.launch_dependents as their first
   // instruction, so the small CTAs start as soon as every heavy CTA is resident (or gone) and fill the other SMs.
   // The two launches write disjoint tiles and both only read what bin_fill_kernel finished before the heavy
-  // launch began, so the dependent launch needs no griddepcontrol.wait.  (A side stream + events did the same but
-  // cost 12 % of the end-to-end step through the Python layer; this costs ~1 % when no bin is heavy.)
+  // launch began, so the dependent launch needs no griddepcontrol.wait at its top.  (A side stream with fork / join
+  // events did the same; one stream keeps the call capturable as a linear chain and costs nothing when no bin is heavy.)
   if (useHeavy) {
     RasterParams ph = p;
     ph.role = 1; ph.pdl = 0;
