@@ -35,6 +35,9 @@ METRIC = BASE.get("metric", "views/sec fwd+bwd at 1024^2, 70k tris")
 UNIT = "views/s"
 WORKLOAD = dict(rings=187, segments=188, cameras=8, width=1024, height=1024, tex=64)
 INPUT_KEYS = ("vertex_pos", "vertex_color", "texture", "sh_coeff", "target_image", "extrinsics", "intrinsics")
+# the SAME string in both arms (the driver compares the two config objects)
+WORKLOAD_NAME = ("config2: UV-sphere 34970 verts / 69936 tris, 8 ring cameras, 1024x1024, ~52% coverage, vertexColor+shaded, "
+                 "fwd+bwd (grads wrt positions, colours, SH), B=1 (8 views) per GPU per step")
 
 
 def peaks():
@@ -345,7 +348,50 @@ def run_ours(args, rank, world, local_rank):
         if not abs(float(loss_host) - float(chk_loss)) <= 1e-4 * max(1.0, abs(float(chk_loss))):
             raise SystemExit("e2e check failed: loss of the replayed step differs from the eager one")
         e2e["checked"] = "loss and gradients read back by the last timed step equal an eager step on the same inputs (rel-L2 <= 1e-4)"
+    # ---- sequential latency: what a fit loop gets, where step i+1's inputs depend on step i's gradients.  ONE slot,
+    # everything on one stream, no cross-step overlap: upload -> captured step -> read-back -> host waits, every step ----
+    sl = slots[0]
+
+    def latency_step():
+        for k, v in host.items():
+            sl.inp[k].copy_(v, non_blocking=True)
+        if sl.graph is not None:
+            sl.graph.replay()
+            loss, grads = sl.loss, sl.grads
+        else:
+            loss, grads = user_step(sl.inp)
+        if world > 1:
+            sharding.allreduce_shared_grads([grads[2], grads[1]])
+        for k, g in zip(GRAD_KEYS, grads):
+            out_host[k].copy_(g, non_blocking=True)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the host holds loss and gradients before it prepares the next step
+
+    for _ in range(5):
+        latency_step()
+    ms_lat = timed(latency_step, args.steps)
+    e2e["latency"] = {"value": round(world * V * args.steps / (ms_lat * 1e-3), 2), "unit": UNIT, "ms_per_step": round(ms_lat / args.steps, 4),
+                      "mode": "one slot, one stream, host synchronises after every step (upload -> step -> read-back strictly in sequence): "
+                              "the dependency a fit loop has; `value` above is the pipelined throughput of independent steps"}
+
     clocks = sampler.stop() if sampler else None
+    # ---- untimed parity leg: the benched configuration against the reference's own CUDA core (Oracle 1), when shipped ----
+    parity = None
+    if rank == 0:
+        try:
+            from oracle import parity as opar, ref as oref
+            if oref.available():
+                res, _, _, _, _ = opar.check_scene(sc, "vertexColor", "shaded", renderer=r, render_grad=G, dev=dev)
+                parity = {"status": "pass", "against": "oracle/_ref/libgvv_ref.so (the reference's kernels compiled unmodified for sm_100a), same inputs, same GPU",
+                          "protocol": "camera matrices, projected vertices, vertex normals, barycentrics, render buffer bit-equal; face buffer equal up to proven "
+                                      "exact depth ties; gradients rel-L2 <= 1e-4, or -- position gradient -- below half of the reference's own fp32 error against the "
+                                      "fp64 evaluation of its formulas (oracle/parity.py)", **{k: (round(v, 9) if isinstance(v, float) else v) for k, v in res.items()}}
+            else:
+                parity = {"status": "unavailable", "reason": "oracle/_ref/libgvv_ref.so not shipped"}
+        except AssertionError as e:
+            parity = {"status": "FAIL", "reason": str(e)[:300]}
+        except Exception as e:
+            parity = {"status": "error", "reason": repr(e)[:300]}
     cpu_baseline = None
     if rank == 0 and world == 1:
         cpu_baseline = cpu_port_baseline(sc, seconds_budget=20.0)
@@ -371,12 +417,11 @@ def run_ours(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "config2: UV-sphere 34970 verts / 69936 tris, 8 ring cameras, 1024x1024, ~52% coverage, vertexColor+shaded, "
-                                       "fwd+bwd (grads wrt positions, colours, SH), B=1 (8 views) per GPU per step",
+                "config": {"workload": WORKLOAD_NAME,
                            "views_per_step_per_gpu": V, "tile": args.tile or 32,
                            "l2": "no explicit flush: a step streams ~300 MB of buffers (192 MB outputs + 100 MB render gradient) through a 126 MB L2",
                            "collective": "none" if world == 1 else "1 NCCL all-reduce/step of shared SH + colour gradients (%d B)" % ((C * 27 + N * 3) * 4)},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
         print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -421,7 +466,7 @@ def run_reference(args, rank, world, local_rank):
     from oracle import ref as oref
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config2 (same inputs as the ours arm), B=1 (8 views) per step"}}
+            "config": {"workload": WORKLOAD_NAME, "views_per_step_per_gpu": C}}
     try:
         import torch
         have_gpu = torch.cuda.is_available()

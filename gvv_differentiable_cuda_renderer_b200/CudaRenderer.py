@@ -40,7 +40,12 @@ def _get_handle(faces, texcoords, N, C, U, V, albedo, shading, ifs, tfs, normal_
             h.set_option("texture_bilinear", 1)
         _HANDLE_CACHE[key] = h
         while len(_HANDLE_CACHE) > _HANDLE_CACHE_MAX:
-            _HANDLE_CACHE.popitem(last=False)[1].close()
+            # Eviction only drops the cache's reference: layers (self._handle) and pending autograd graphs
+            # (ctx.handle) may still hold the handle, and gvv_destroy runs from NativeRenderer.__del__ when the
+            # last of them lets go.  Closing here would turn a later .backward() into gvv_backward(NULL).
+            old = _HANDLE_CACHE.popitem(last=False)[1]
+            for k in [k for k, v in _IDENT_CACHE.items() if v[2] is old]:
+                del _IDENT_CACHE[k]
     else:
         _HANDLE_CACHE.move_to_end(key)
     if len(_IDENT_CACHE) > 4 * _HANDLE_CACHE_MAX:
@@ -50,9 +55,9 @@ def _get_handle(faces, texcoords, N, C, U, V, albedo, shading, ifs, tfs, normal_
 
 
 def clear_handle_cache():
+    """Drops every cached handle; each is destroyed when its last user (layer / autograd graph) releases it."""
     _IDENT_CACHE.clear()
-    while _HANDLE_CACHE:
-        _HANDLE_CACHE.popitem()[1].close()
+    _HANDLE_CACHE.clear()
 
 
 class _CudaRendererFn(torch.autograd.Function):
@@ -150,7 +155,7 @@ class CudaRendererGpu:
         if device is None:
             device = vertexPos_input.device if isinstance(vertexPos_input, torch.Tensor) and vertexPos_input.is_cuda \
                 else torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
-        self.device = torch.device(device)
+        self.device = _native.normalize_device(device)
         self.vertexPos_input = _as_cuda(vertexPos_input, self.device, "vertexPos_input")
         self.vertexColor_input = _as_cuda(vertexColor_input, self.device, "vertexColor_input")
         self.texture_input = _as_cuda(texture_input, self.device, "texture_input")

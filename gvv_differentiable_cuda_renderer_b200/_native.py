@@ -51,7 +51,7 @@ class gvv_desc(ctypes.Structure):
 _lib = None
 
 # every symbol include/gvv_b200.h declares
-EXPORTS = ["gvv_create", "gvv_destroy", "gvv_forward", "gvv_backward", "gvv_last_error", "gvv_launch_count",
+EXPORTS = ["gvv_create", "gvv_destroy", "gvv_reserve", "gvv_forward", "gvv_backward", "gvv_last_error", "gvv_launch_count",
            "gvv_debug_copy", "gvv_debug_eval", "gvv_set_option", "gvv_bench_atomics",
            "gvv_kernel_count", "gvv_kernel_name", "gvv_kernel_times",
            "gvv_gaussian_smooth", "gvv_image_gradient", "gvv_set_target_gradient"]
@@ -69,6 +69,8 @@ def lib():
         L.gvv_create.restype = ctypes.c_int
         L.gvv_destroy.argtypes = [vp]
         L.gvv_destroy.restype = ctypes.c_int
+        L.gvv_reserve.argtypes = [vp, i32, vp]
+        L.gvv_reserve.restype = ctypes.c_int
         L.gvv_forward.argtypes = [vp, i32, i32, i32] + [vp] * 7 + [vp] * 6 + [vp]
         L.gvv_forward.restype = ctypes.c_int
         L.gvv_backward.argtypes = [vp, i32, i32, i32] + [vp] * 12 + [vp] * 4 + [vp]
@@ -124,6 +126,23 @@ def _f32(t, name, device):
     return t.contiguous()
 
 
+def normalize_device(device):
+    """torch.device with an explicit index: 'cuda' means the current device (torch never compares cuda == cuda:0)."""
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise GvvError(f"the renderer lives on a CUDA device, not on {device} (there is no CPU path)")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    return device
+
+
+def _numel(t, n, name):
+    if t is not None and t.numel() != n:
+        raise GvvError(f"{name} has {t.numel()} elements, expected {n}")
+
+
 class _NullCtx:
     def __enter__(self):
         return None
@@ -137,7 +156,7 @@ _NULL = _NullCtx()
 
 def _device_ctx(dev):
     """torch.cuda.device(dev) only when dev is not already current (the context manager costs ~10 us per call)."""
-    return _NULL if torch.cuda.current_device() == (dev.index or 0) else torch.cuda.device(dev)
+    return _NULL if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
 
 
 class NativeRenderer:
@@ -151,7 +170,7 @@ class NativeRenderer:
             raise GvvError("INVALID SHADING MODE")       # CudaRenderer.cpp:67-71
         if not torch.cuda.is_available():
             raise GvvError("CUDA device required: the renderer has no CPU fallback")
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = normalize_device(device)
         f = np.ascontiguousarray(np.asarray(faces, dtype=np.int32).reshape(-1))
         if f.size % 3:
             raise GvvError("No triangular faces!")        # CUDABasedRasterization.cpp:38-41
@@ -166,7 +185,7 @@ class NativeRenderer:
         self.compute_normal_map = bool(compute_normal_map)
         d = gvv_desc(f.ctypes.data, self.F, t.ctypes.data if t is not None else None, self.N, self.C, self.W, self.H,
                      ALBEDO_MODES[albedo_mode], SHADING_MODES[shading_mode], int(image_filter_size),
-                     int(texture_filter_size), int(self.compute_normal_map), self.device.index or 0)
+                     int(texture_filter_size), int(self.compute_normal_map), self.device.index)
         h = ctypes.c_void_p()
         _check(lib().gvv_create(ctypes.byref(d), ctypes.byref(h)), "gvv_create")
         self._h = h
@@ -181,6 +200,11 @@ class NativeRenderer:
             self.close()
         except Exception:
             pass
+
+    def reserve(self, max_batch):
+        """Allocate the scratch for calls of up to max_batch batch elements now (before CUDA-graph capture)."""
+        with _device_ctx(self.device):
+            _check(lib().gvv_reserve(self._h, int(max_batch), self._stream()), "gvv_reserve")
 
     def set_option(self, key, value):
         _check(lib().gvv_set_option(self._h, key.encode(), int(value)), "gvv_set_option")
@@ -204,9 +228,12 @@ class NativeRenderer:
         # B, texH, texW come from the texture tensor, as in CudaRenderer.cpp:207-209
         B, texH, texW = int(texture.shape[0]), int(texture.shape[1]), int(texture.shape[2])
         C, N, W, H = self.C, self.N, self.W, self.H
-        if vertex_pos.numel() != B * N * 3 or sh_coeff.numel() != B * C * 27 or \
-           extrinsics.numel() != B * C * 12 or intrinsics.numel() != B * C * 9:
-            raise GvvError("input tensor sizes do not match batch/cameras/vertices")
+        if texture.dim() != 4 or texture.shape[3] != 3:
+            raise GvvError(f"texture must be [B, texH, texW, 3], got {tuple(texture.shape)}")
+        for t, n, name in ((vertex_pos, B * N * 3, "vertex_pos"), (sh_coeff, B * C * 27, "sh_coeff"),
+                           (extrinsics, B * C * 12, "extrinsics"), (intrinsics, B * C * 9, "intrinsics"),
+                           (vertex_color, B * N * 3, "vertex_color"), (target_image, B * C * H * W * 3, "target_image")):
+            _numel(t, n, name)
         o = dict(device=dev, dtype=torch.float32)
         with _device_ctx(dev):
             bary = torch.empty((B, C, H, W, 2), **o)
@@ -233,8 +260,25 @@ class NativeRenderer:
         tensors (entries may be None) -- e.g. views into ONE flat buffer, so that the gradients of parameters shared
         across ranks can be all-reduced in place without packing (sharding.allreduce_shared_grads)."""
         dev = self.device
-        B, texH, texW = int(texture.shape[0]), int(texture.shape[1]), int(texture.shape[2])
-        C, N = self.C, self.N
+        # B comes from vertex_pos like in the reference's gradient op (CudaRendererGrad.cpp:195; the forward takes it
+        # from the texture, CudaRenderer.cpp:207); where the reference would overrun on a mismatch, this raises
+        C, N, W, H = self.C, self.N, self.W, self.H
+        if vertex_pos.dim() < 2 or vertex_pos.numel() % (N * 3):
+            raise GvvError(f"vertex_pos must be [B, {N}, 3], got {tuple(vertex_pos.shape)}")
+        B, texH, texW = vertex_pos.numel() // (N * 3), int(texture.shape[1]), int(texture.shape[2])
+        if texture.dim() != 4 or texture.shape[3] != 3 or int(texture.shape[0]) != B:
+            raise GvvError(f"texture must be [{B}, texH, texW, 3] (batch of vertex_pos), got {tuple(texture.shape)}")
+        if face.dtype != torch.int32:
+            raise GvvError(f"face_buffer must be int32, got {face.dtype}")
+        if face.device != dev:
+            raise GvvError(f"face_buffer is on {face.device}, the renderer lives on {dev}")
+        P = B * C * H * W
+        for t, n, name in ((render_grad, P * 3, "render_buffer_grad"), (target_grad, P * 3, "target_buffer_grad"),
+                           (vertex_pos, B * N * 3, "vertex_pos"), (vertex_color, B * N * 3, "vertex_color"),
+                           (sh_coeff, B * C * 27, "sh_coeff"), (target_image, P * 3, "target_image"),
+                           (vertex_normal, B * C * N * 3, "vertex_normal"), (bary, P * 2, "barycentric_buffer"),
+                           (face, P, "face_buffer"), (extrinsics, B * C * 12, "extrinsics"), (intrinsics, B * C * 9, "intrinsics")):
+            _numel(t, n, name)
         args = [_f32(t, n, dev) for t, n in [(render_grad, "render_buffer_grad"), (vertex_pos, "vertex_pos"),
                                               (vertex_color, "vertex_color"), (texture, "texture"),
                                               (sh_coeff, "sh_coeff"), (target_image, "target_image"),
@@ -312,7 +356,7 @@ def image_gradient(image, filter_size):
     n = image.numel() // (H * W * 3)
     du, dv = torch.empty_like(image), torch.empty_like(image)
     with torch.cuda.device(image.device):
-        _check(lib().gvv_image_gradient(image.device.index or 0, n, H, W, int(filter_size), _ptr(image), _ptr(du), _ptr(dv),
+        _check(lib().gvv_image_gradient(image.device.index, n, H, W, int(filter_size), _ptr(image), _ptr(du), _ptr(dv),
                                         ctypes.c_void_p(torch.cuda.current_stream(image.device).cuda_stream)), "gvv_image_gradient")
     return du, dv
 
@@ -328,6 +372,6 @@ def gaussian_smooth(image, taps):
     n = image.numel() // (H * W * 3)
     tmp, out = torch.empty_like(image), torch.empty_like(image)
     with torch.cuda.device(image.device):
-        _check(lib().gvv_gaussian_smooth(image.device.index or 0, n, H, W, taps.size // 2, taps.ctypes.data, _ptr(image), _ptr(tmp), _ptr(out),
+        _check(lib().gvv_gaussian_smooth(image.device.index, n, H, W, taps.size // 2, taps.ctypes.data, _ptr(image), _ptr(tmp), _ptr(out),
                                          ctypes.c_void_p(torch.cuda.current_stream(image.device).cuda_stream)), "gvv_gaussian_smooth")
     return out

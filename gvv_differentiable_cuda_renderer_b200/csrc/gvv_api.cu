@@ -53,12 +53,26 @@ static void set_tile(gvv_renderer* h, int tile) {
   h->nT = h->tilesX * h->tilesY;
 }
 
-// Scratch is sized for the largest batch seen; growing it is the only time a call allocates.
+// Scratch is sized for the largest batch seen (or reserved with gvv_reserve); growing it is the only time a call
+// allocates.  Growth frees and re-allocates every scratch buffer, so it must not happen while anything can still
+// use the old ones:
+//   - the whole device is synchronised first (work of this handle on ANY stream, not only the caller's);
+//   - it is refused while `st` is being captured (allocation is illegal there) and once the handle has been used
+//     under stream capture -- the captured graphs have the old scratch pointers baked in, and replaying them
+//     after a re-allocation would read and write freed memory.  Reserve the largest batch before capturing.
 static int ensure_scratch(gvv_renderer* h, int B, cudaStream_t st) {
   Scratch& s = h->s;
   const int V = B * h->C;
-  if (V <= s.capViews && B <= s.capBatch) return GVV_OK;
-  CK(cudaStreamSynchronize(st));
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
+  if (V <= s.capViews && B <= s.capBatch) { if (capturing) h->captured = 1; return GVV_OK; }
+  if (capturing)
+    return fail(GVV_EINVAL, "scratch for batch %d is not allocated and the stream is being captured: call gvv_reserve (or run one eager call) first", B);
+  if (h->captured)
+    return fail(GVV_EINVAL, "batch %d exceeds the scratch (batch %d) that CUDA graphs captured on this handle have baked in: "
+                            "gvv_reserve the largest batch before capturing, or use another handle", B, s.capBatch);
+  CK(cudaDeviceSynchronize());
   free_scratch(s);
   const size_t N = h->N, F = h->F, nT = h->nT;
   cudaError_t e = cudaSuccess;
@@ -111,6 +125,9 @@ extern "C" int gvv_create(const gvv_desc* d, gvv_handle* out) {
   if (d->width <= 0) return fail(GVV_EINVAL, "render_resolution_u not set!");
   if (d->height <= 0) return fail(GVV_EINVAL, "render_resolution_v not set!");
   if (d->width > 65535 || d->height > 65535) return fail(GVV_EINVAL, "render resolution above 65535 is not supported");
+  // the per-view tile histogram of bin_scan_kernel lives in shared memory: at most kMaxTiles tiles of 32 x 32 pixels
+  if ((long long)((d->width + 31) / 32) * ((d->height + 31) / 32) > kMaxTiles)
+    return fail(GVV_EINVAL, "render resolution %d x %d needs more than %d tiles of 32 x 32 pixels: not supported", d->width, d->height, kMaxTiles);
   if (d->albedo_mode < 0 || d->albedo_mode > 4) return fail(GVV_EINVAL, "INVALID ALBEDO MODE");
   if (d->shading_mode < 0 || d->shading_mode > 1) return fail(GVV_EINVAL, "INVALID SHADING MODE");
   if (d->num_faces < 0 || (d->num_faces > 0 && !d->faces)) return fail(GVV_EINVAL, "faces missing");
@@ -193,6 +210,13 @@ extern "C" int gvv_create(const gvv_desc* d, gvv_handle* out) {
   return GVV_OK;
 }
 
+extern "C" int gvv_reserve(gvv_handle h, int32_t max_batch, void* stream) {
+  if (!h) return fail(GVV_EINVAL, "gvv_reserve: null handle");
+  if (max_batch <= 0) return fail(GVV_EINVAL, "gvv_reserve: batch must be positive");
+  CK(cudaSetDevice(h->device));
+  return ensure_scratch(h, max_batch, (cudaStream_t)stream);
+}
+
 extern "C" int gvv_destroy(gvv_handle h) {
   if (!h) return GVV_OK;
   cudaSetDevice(h->device);
@@ -208,6 +232,9 @@ extern "C" int gvv_set_option(gvv_handle h, const char* key, int32_t value) {
   if (!h || !key) return fail(GVV_EINVAL, "gvv_set_option: null argument");
   if (!strcmp(key, "tile")) {
     if (value != 16 && value != 32) return fail(GVV_EINVAL, "tile must be 16 or 32");
+    if ((long long)((h->W + value - 1) / value) * ((h->H + value - 1) / value) > kMaxTiles)
+      return fail(GVV_EINVAL, "tile %d gives more than %d tiles at %d x %d: not supported", value, kMaxTiles, h->W, h->H);
+    if (value != h->tile && h->captured) return fail(GVV_EINVAL, "tile cannot change after the handle was used under stream capture");
     if (value != h->tile) {
       cudaSetDevice(h->device);
       cudaDeviceSynchronize();
@@ -223,7 +250,7 @@ extern "C" int gvv_set_option(gvv_handle h, const char* key, int32_t value) {
   if (!strcmp(key, "batch_div")) { if (value < 1) return fail(GVV_EINVAL, "batch_div must be >= 1"); h->batchDiv = value; return GVV_OK; }
   if (!strcmp(key, "cta_threads")) { if (value != 128 && value != 256) return fail(GVV_EINVAL, "cta_threads must be 128 or 256"); h->ctaThreads = value; return GVV_OK; }
   if (!strcmp(key, "span_z")) { if (value < 0 || value > 2) return fail(GVV_EINVAL, "span_z must be 0 (off), 1 (both passes) or 2 (far pass only)"); h->spanZ = value; return GVV_OK; }
-  if (!strcmp(key, "cta_trace")) { cudaSetDevice(h->device); cudaDeviceSynchronize(); free_scratch(h->s); h->ctaTrace = value ? 1 : 0; return GVV_OK; }   // scratch is re-allocated by the next call
+  if (!strcmp(key, "cta_trace")) { if (h->captured) return fail(GVV_EINVAL, "cta_trace cannot change after the handle was used under stream capture"); cudaSetDevice(h->device); cudaDeviceSynchronize(); free_scratch(h->s); h->ctaTrace = value ? 1 : 0; return GVV_OK; }   // scratch is re-allocated by the next call
   if (!strcmp(key, "texture_bilinear")) { h->texBilinear = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "chain")) { h->chain = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "resolve_prefetch")) { h->resolvePrefetch = value ? 1 : 0; return GVV_OK; }
@@ -401,7 +428,7 @@ extern "C" int gvv_debug_eval(gvv_handle h, int32_t n, const int32_t* queries, i
 }
 
 static const char* kKernelNames[K_NUM_SLOTS] = {"camera_kernel", "vertex_kernel", "bin_count_kernel", "bin_scan_kernel",
-                                                "bin_fill_kernel", "raster_kernel", "zero_kernel", "pixel_grad_kernel",
+                                                "bin_fill_kernel", "raster_kernel", "prep_kernel", "pixel_grad_kernel",
                                                 "normal_term_kernel", "normal_map_kernel"};
 
 extern "C" int32_t gvv_kernel_count(void) { return K_NUM_SLOTS; }

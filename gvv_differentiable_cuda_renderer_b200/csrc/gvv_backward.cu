@@ -4,8 +4,8 @@
 // 157 registers, ~214 scalar float atomics per covered pixel, 27 of them on the same 27 SH
 // addresses for every pixel of a camera.  Here, for all B*C views in one go:
 //
-//   camera_kernel        (shared with the forward)                                   (ref :17-61)
-//   zero_kernel          all four gradient outputs + the vertex-normal gradient      (ref :68-107)
+//   prep_kernel          camera records (ref :17-61), zero fill of all four gradient outputs + the vertex-normal
+//                        gradient (ref :68-107), repack of the caller's 12-byte vertex arrays to float4
 //   pixel_grad_kernel    one warp per 32-pixel scanline segment.  The 27 per-vertex values of a
 //                        pixel (9 colour, 9 position, 9 vertex-normal gradient) are transposed
 //                        through shared memory so that lane j sums value j over each run of
@@ -35,61 +35,7 @@ __device__ __forceinline__ V3 ldv3(const float* __restrict__ p, size_t i) { retu
 // ------------------------------------------------------------------------------------------------
 struct ZeroArgs { float* p[5]; long long n[5]; };
 
-__global__ void zero_kernel(ZeroArgs z) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-#pragma unroll
-  for (int r = 0; r < 5; ++r) {
-    float* p = z.p[r];
-    if (!p) continue;
-    const long long n = z.n[r];
-    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-      float4* p4 = reinterpret_cast<float4*>(p);
-      const long long n4 = n >> 2;
-      for (long long i = t0; i < n4; i += stride) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (long long i = (n4 << 2) + t0; i < n; i += stride) p[i] = 0.f;
-    } else {
-      for (long long i = t0; i < n; i += stride) p[i] = 0.f;
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// d(alpha*a + beta*b)/d(v0,v1,v2) for the barycentrics of the ray/plane hit: the product
-// [alpha beta gamma] * dJBCDVerpos (RendererUtil.h:670-861) with the third row = -(row0+row1)
-// folded into alpha,beta.  The reference builds the 3x9 Jacobian column by column; this is the
-// same derivative in reverse mode.  Early-out conditions as RendererUtil.h:682-685.
-__device__ __forceinline__ void bary_vjp(V3 o, V3 d, V3 v0, V3 v1, V3 v2, float alpha, float beta, V3& g0, V3& g1, V3& g2) {
-  g0 = g1 = g2 = v3(0.f, 0.f, 0.f);
-  const V3 e01 = v1 - v0, e02 = v2 - v0;
-  const V3 N = cross(e01, e02);
-  const float D = dot(N, N);
-  const float nd = dot(d, N);
-  const float il = rsqrtf(dot(d, d)), in = rsqrtf(D);
-  if (fabsf(dot(il * d, in * N)) < 0.001f || fabsf(D * D) < 0.001f) return;
-  const V3 w = v0 - o;
-  const float t = dot(w, N) / nd;
-  const V3 P = o + t * d;
-  const V3 E1 = v2 - v1, p1 = P - v1, C1 = cross(E1, p1);
-  const V3 E2 = v0 - v2, p2 = P - v2, C2 = cross(E2, p2);
-  const float A = dot(N, C1), Bn = dot(N, C2);
-  const float Ab = alpha / D, Bb = beta / D;
-  const float Db = -(alpha * A + beta * Bn) / (D * D);
-  V3 Nb = Ab * C1 + Bb * C2 + (2.f * Db) * N;
-  const V3 C1b = Ab * N, C2b = Bb * N;
-  const V3 E1b = cross(p1, C1b), p1b = cross(C1b, E1);
-  const V3 E2b = cross(p2, C2b), p2b = cross(C2b, E2);
-  const V3 Pb = p1b + p2b;
-  const float tb = dot(Pb, d);
-  const float mb = tb / nd;
-  const float ndb = -tb * t / nd;
-  Nb = Nb + mb * w + ndb * d;
-  const V3 e01b = cross(e02, Nb), e02b = cross(Nb, e01);
-  g0 = E2b + mb * N - e01b - e02b;
-  g1 = e01b - p1b - E1b;
-  g2 = e02b - p2b + E1b - E2b;
-}
-
 struct PixelParams {
   const float *render_grad, *target_grad, *vertex_pos, *vertex_color, *texture, *sh_coeff, *target_image,
       *vertex_normal, *bary, *texcoords, *target_du, *target_dv;
@@ -112,6 +58,9 @@ constexpr int kRow = 36;    // 32 pixels + 4 pad: a quarter-warp's float4 reads 
 // (gradients are compared to rel-L2 1e-4; the visibility-critical ray uses the exact functions).
 __device__ __forceinline__ float rcpf(float x) { return __frcp_rn(x); }
 
+// d(alpha*a + beta*b)/d(v0,v1,v2) for the barycentrics of the ray/plane hit: the product [alpha beta gamma] *
+// dJBCDVerpos (RendererUtil.h:670-861) with the third row = -(row0+row1) folded into alpha, beta.  The reference
+// builds the 3x9 Jacobian column by column; this is the same derivative in reverse mode.  Early-outs as :682-685.
 __device__ __forceinline__ void bary_vjp_fast(V3 o, V3 d, V3 v0, V3 v1, V3 v2, float alpha, float beta, V3& g0, V3& g1, V3& g2) {
   g0 = g1 = g2 = v3(0.f, 0.f, 0.f);
   const V3 e01 = v1 - v0, e02 = v2 - v0;

@@ -1117,7 +1117,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const int maxLog = a.splitUnit > 0 ? (a.tile == 32 ? 3 : 2) : 0;
   static unsigned long long scanAttr = 0;
   if (first_use_on_device(&scanAttr)) cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  if ((size_t)a.nT * sizeof(int) > 160 * 1024) return -1;   // 40960 tiles = e.g. 6400 x 6400 pixels at 32 x 32; larger grids are not supported
+  if (a.nT > kMaxTiles) return -1;   // rejected by gvv_create / gvv_set_option("tile") already
   launch_chained(a.chain, bin_scan_kernel, dim3(V + (V + 1023) / 1024), dim3(1024), a.nT * sizeof(int), st, a.s.tileCount, a.s.tileOffset, a.s.tileOrder, a.s.tileMinK, a.s.tileMaxK, a.s.tileThr,
                  a.nT, a.tilesX, nItems, a.splitUnit > 0 ? a.splitUnit : 1, maxLog,
                  useHeavy ? a.heavyThr : 0, kHeavySlots, a.heavyMode == 2 ? -1 : max(1, a.ctaSlots / V), a.spreadEmpty, a.extrinsics, a.intrinsics, a.s.cams, V);

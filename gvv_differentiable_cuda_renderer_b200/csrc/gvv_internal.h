@@ -11,6 +11,7 @@ namespace gvv {
 // which every tile of that view scans; everything else is appended to per-tile bins.  This bounds
 // the bin pool by F*kMaxSmallTiles entries per view without ever reading a count back to the host.
 constexpr int kMaxSmallTiles = 16;
+constexpr int kMaxTiles = 40960;       // bin_scan_kernel keeps a view's tile histogram in shared memory (160 KB): e.g. 6400 x 6400 pixels at 32 x 32
 constexpr int kSmemHistTiles = 12288;  // largest tile grid handled with shared-memory histograms (3840x2160 at 32x32 = 8160 tiles; bin_fill needs 16 B per tile: 192 KB)
 
 struct Scratch {
@@ -65,6 +66,7 @@ struct gvv_renderer {
   int albedo = 0, shading = 0, imgFilter = 1, texFilter = 1, computeNormalMap = 0;
   int tile = 32, tilesX = 0, tilesY = 0, nT = 0;
   const float* targetDu = nullptr; const float* targetDv = nullptr;   // caller-owned precomputed target-image gradient (gvv_set_target_gradient)
+  int captured = 0;           // the handle has been used while its stream was being captured: the scratch pointers are baked into CUDA graphs
   int chain = 1;              // launch the kernels of a call as a programmatic dependent-launch chain
   int resolvePrefetch = 0;    // raster: L1 prefetch sweep of the resolve stage's vertex gathers (measured slower: 0.272 -> 0.282 ms)
   int texBilinear = 0;        // non-default: bilinear texture fetch + weighted 4-texel gradient scatter (the variants the reference has commented out)

@@ -15,40 +15,48 @@
 
 namespace gvv {
 
+// The reference builds the table ON THE HOST (x86-64, SSE scalar fp32, no FMA contraction): every operation below
+// is therefore a separately rounded IEEE single operation in the reference's source order, pinned with __f*_rn
+// intrinsics so that nvcc cannot fuse them -- the (a, b, c) of a texel are then bit-identical to the host's.
 struct H3 { float x, y, z; };
 __device__ __forceinline__ H3 h3(float x, float y, float z) { H3 r; r.x = x; r.y = y; r.z = z; return r; }
-__device__ __forceinline__ H3 hsub(H3 a, H3 b) { return h3(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ float hdot(H3 a, H3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ H3 hcross(H3 a, H3 b) { return h3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ H3 hsub(H3 a, H3 b) { return h3(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
+__device__ __forceinline__ H3 hdiv(H3 a, float s) { return h3(__fdiv_rn(a.x, s), __fdiv_rn(a.y, s), __fdiv_rn(a.z, s)); }
+__device__ __forceinline__ float hdot(H3 a, H3 b) {          // cutil_math.h:1119-1122, left to right
+  return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ H3 hcross(H3 a, H3 b) {           // cutil_math.h:1295-1298
+  return h3(__fsub_rn(__fmul_rn(a.y, b.z), __fmul_rn(a.z, b.y)), __fsub_rn(__fmul_rn(a.z, b.x), __fmul_rn(a.x, b.z)),
+            __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
 
 // rayTriangleIntersectHost (CUDABasedRasterization.cpp:156-235) for the fixed ray of a texel
 __device__ __forceinline__ bool texel_hit(float px, float py, H3 v0, H3 v1, H3 v2, float& a, float& b) {
-  v0 = h3(v0.x / 1000.f, v0.y / 1000.f, v0.z / 1000.f);
-  v1 = h3(v1.x / 1000.f, v1.y / 1000.f, v1.z / 1000.f);
-  v2 = h3(v2.x / 1000.f, v2.y / 1000.f, v2.z / 1000.f);
-  const H3 orig = h3(px / 1000.f, py / 1000.f, 1.f / 1000.f);
+  v0 = hdiv(v0, 1000.f); v1 = hdiv(v1, 1000.f); v2 = hdiv(v2, 1000.f);
+  const H3 orig = hdiv(h3(px, py, 1.f), 1000.f);
   const H3 dir = h3(0.f, 0.f, -1.f);
   const H3 N = hcross(hsub(v1, v0), hsub(v2, v0));
   const float nd = hdot(dir, N);
   if (fabsf(nd) < 0.0000001f) return false;
-  const float t = (hdot(v0, N) - hdot(orig, N)) / nd;
+  const float t = __fdiv_rn(__fsub_rn(hdot(v0, N), hdot(orig, N)), nd);
   if (t < 0.f) return false;
-  const H3 P = h3(orig.x + t * dir.x, orig.y + t * dir.y, orig.z + t * dir.z);
+  const H3 P = h3(__fadd_rn(orig.x, __fmul_rn(t, dir.x)), __fadd_rn(orig.y, __fmul_rn(t, dir.y)), __fadd_rn(orig.z, __fmul_rn(t, dir.z)));
   if (hdot(N, hcross(hsub(v1, v0), hsub(P, v0))) < 0.f) return false;
   a = hdot(N, hcross(hsub(v2, v1), hsub(P, v1)));
   if (a < 0.f) return false;
   b = hdot(N, hcross(hsub(v0, v2), hsub(P, v2)));
   if (b < 0.f) return false;
   const float den = hdot(N, N);
-  a /= den; b /= den;
+  a = __fdiv_rn(a, den); b = __fdiv_rn(b, den);
   return true;
 }
 
 __device__ __forceinline__ void texel_tri(const float* __restrict__ tc, int f, int texW, int texH, H3& t0, H3& t1, H3& t2) {
   const float* t = tc + (size_t)f * 6;
-  t0 = h3(texW * t[0], texH * (1.f - t[1]), 0.f);
-  t1 = h3(texW * t[2], texH * (1.f - t[3]), 0.f);
-  t2 = h3(texW * t[4], texH * (1.f - t[5]), 0.f);
+  const float w = (float)texW, h = (float)texH;
+  t0 = h3(__fmul_rn(w, t[0]), __fmul_rn(h, __fsub_rn(1.f, t[1])), 0.f);
+  t1 = h3(__fmul_rn(w, t[2]), __fmul_rn(h, __fsub_rn(1.f, t[3])), 0.f);
+  t2 = h3(__fmul_rn(w, t[4]), __fmul_rn(h, __fsub_rn(1.f, t[5])), 0.f);
 }
 
 __global__ void texel_clear_kernel(int* __restrict__ faceTable, int n) {
@@ -83,7 +91,7 @@ __global__ void texel_bary_kernel(const float* __restrict__ tc, int texH, int te
     texel_tri(tc, f, texW, texH, t0, t1, t2);
     float a = 0.f, b = 0.f;
     texel_hit((i % texW) + 0.5f, (i / texW) + 0.5f, t0, t1, t2, a, b);
-    out = make_float4((float)f, a, b, 1.f - a - b);
+    out = make_float4((float)f, a, b, __fsub_rn(__fsub_rn(1.f, a), b));
   }
   table[i] = out;
 }
@@ -98,13 +106,15 @@ __global__ void normal_map_kernel(const float4* __restrict__ table, const int4* 
   const int4 fc = __ldg(faces4 + (int)info.x);
   const float4* vn = vnorm4 + (size_t)b * N;
   const float4 n0 = __ldg(vn + fc.x), n1 = __ldg(vn + fc.y), n2 = __ldg(vn + fc.z);
-  float nx = n0.x * info.y + n1.x * info.z + n2.x * info.w;
-  float ny = n0.y * info.y + n1.y * info.z + n2.y * info.w;
-  float nz = n0.z * info.y + n1.z * info.z + n2.z * info.w;
-  const float len = sqrtf(nx * nx + ny * ny + nz * nz);
-  if (len != 0.f) { nx /= len; ny /= len; nz /= len; }
+  // contraction as in the compiled reference kernel (SASS of renderNormalMapDevice, nvcc 12.9 sm_100a):
+  // fma(c, n2, fma(a, n0, b * n1)), dot = fma(z,z, fma(x,x, y*y)), IEEE sqrt and divides
+  float nx = interp3(info.y, info.z, info.w, n0.x, n1.x, n2.x);
+  float ny = interp3(info.y, info.z, info.w, n0.y, n1.y, n2.y);
+  float nz = interp3(info.y, info.z, info.w, n0.z, n1.z, n2.z);
+  const float len = __fsqrt_rn(dot3x(mk3(nx, ny, nz), mk3(nx, ny, nz)));
+  if (len != 0.f) { nx = __fdiv_rn(nx, len); ny = __fdiv_rn(ny, len); nz = __fdiv_rn(nz, len); }
   float* o = normal_map + ((size_t)b * texels + i) * 3;
-  o[0] = (nx + 1.f) / 2.f; o[1] = (ny + 1.f) / 2.f; o[2] = (nz + 1.f) / 2.f;
+  o[0] = __fmul_rn(__fadd_rn(nx, 1.f), 0.5f); o[1] = __fmul_rn(__fadd_rn(ny, 1.f), 0.5f); o[2] = __fmul_rn(__fadd_rn(nz, 1.f), 0.5f);
 }
 
 int launch_build_texel_table(const float* texcoords, int F, int texH, int texW, float4* table, cudaStream_t st) {

@@ -29,9 +29,11 @@ class CameraReader:
         self.numberOfCameras = len(self.extrinsics) // 12
         K = np.asarray(self.intrinsics, dtype=np.float64).reshape(self.numberOfCameras, 3, 3)
         for c in range(self.numberOfCameras):
-            su, sv = renderResolutionU / self.originalSizeU[c], renderResolutionV / self.originalSizeV[c]
-            K[c, 0, 0] *= su; K[c, 0, 2] *= su
-            K[c, 1, 1] *= sv; K[c, 1, 2] *= sv
+            # same operation order as the reference (divide by the calibration size, then multiply, :41-46), in float64
+            K[c, 0, 0] = (K[c, 0, 0] / self.originalSizeU[c]) * renderResolutionU
+            K[c, 1, 1] = (K[c, 1, 1] / self.originalSizeV[c]) * renderResolutionV
+            K[c, 0, 2] = (K[c, 0, 2] / self.originalSizeU[c]) * renderResolutionU
+            K[c, 1, 2] = (K[c, 1, 2] / self.originalSizeV[c]) * renderResolutionV
         self.intrinsics = list(K.flatten())
 
     def extrinsics_array(self):

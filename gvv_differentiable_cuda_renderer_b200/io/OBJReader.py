@@ -22,11 +22,12 @@ import numpy as np
 def _load_image_rgb01(path):
     try:
         from PIL import Image
-        return np.asarray(Image.open(path).convert("RGB"), dtype=np.float32) / 255.0
+        # uint8 / 255.0 in float64 like the reference (cv2 image / 255.0, OBJReader.py:203-205), then fp32 as the op casts it
+        return (np.asarray(Image.open(path).convert("RGB"), dtype=np.float64) / 255.0).astype(np.float32)
     except ImportError:
         import cv2
         img = cv2.imread(path)
-        return cv2.cvtColor(img, cv2.COLOR_BGR2RGB).astype(np.float32) / 255.0
+        return (cv2.cvtColor(img, cv2.COLOR_BGR2RGB) / 255.0).astype(np.float32)
 
 
 class OBJReader:

@@ -24,7 +24,12 @@
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default
  *     stream); the calls never synchronise the host and never allocate once the scratch for
  *     the largest batch seen so far exists;
- *   - a handle is not re-entrant (same as one TF kernel instance);
+ *   - a handle is not re-entrant (same as one TF kernel instance) and is used from ONE stream at a time: its scratch
+ *     (projected vertices, bins, self-cleaning tile counters) is shared by all calls, so calls on different streams
+ *     must be ordered by the caller (events) -- concurrent streams need one handle each;
+ *   - scratch grows (device-wide synchronisation, free + allocate) when a call's batch exceeds every batch seen
+ *     before.  gvv_reserve sizes it up front.  Growth is refused (GVV_EINVAL) while the stream is being captured
+ *     and after the handle has been used under capture: CUDA graphs bake the scratch pointers in;
  *   - return value 0 = success; otherwise a GVV_E* code and gvv_last_error() (thread-local)
  *     describes it.  The library never calls exit() and never throws across the ABI.
  */
@@ -82,6 +87,12 @@ typedef struct gvv_renderer* gvv_handle;
 
 int gvv_create(const gvv_desc* desc, gvv_handle* out);
 int gvv_destroy(gvv_handle h);
+
+/* Allocates the scratch for calls of up to `max_batch` batch elements now (replaces the scratch cudaMallocs of the
+ * reference constructors, CUDABasedRasterization.cpp:26-101, which size theirs for ONE batch element because the op
+ * loops over the batch on the host).  Call it before capturing gvv_forward / gvv_backward into a CUDA graph with a
+ * batch larger than any eager call has used.  Synchronises the device when it has to (re)allocate. */
+int gvv_reserve(gvv_handle h, int32_t max_batch, void* stream);
 
 /* Forward: inputs in0..in6 and outputs out0..out5 of CudaRendererGpu (CudaRenderer.cpp:5-21).
  *   vertex_pos   [B,N,3]   vertex_color [B,N,3]   texture [B,texH,texW,3]   sh_coeff [B,C,27]

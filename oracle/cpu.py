@@ -7,6 +7,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgvv_oracle.so")
+LIB64_PATH = os.path.join(_HERE, "libgvv_oracle64.so")      # same source, -DGVVO_FP64: every float is a double
 SRC = os.path.join(_HERE, "gvv_oracle.cpp")
 ALBEDO = {"vertexColor": 0, "textured": 1, "normal": 2, "lighting": 3, "foregroundMask": 4}
 SHADING = {"shaded": 0, "shadeless": 1}
@@ -16,6 +17,9 @@ def build(force=False):
     if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(SRC):
         # -ffp-contract=off: plain IEEE fp32, no FMA contraction (the GPU contracts; see header of the .cpp)
         subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=c++17", "-o", LIB_PATH, SRC],
+                       check=True)
+    if force or not os.path.exists(LIB64_PATH) or os.path.getmtime(LIB64_PATH) < os.path.getmtime(SRC):
+        subprocess.run(["g++", "-O2", "-DGVVO_FP64", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=c++17", "-o", LIB64_PATH, SRC],
                        check=True)
     return LIB_PATH
 
@@ -36,6 +40,21 @@ def _load():
         L.gvvo_max_threads.restype = i
         _lib = L
     return _lib
+
+
+_lib64 = None
+
+
+def _load64():
+    global _lib64
+    if _lib64 is None:
+        build()
+        L = ctypes.CDLL(LIB64_PATH)
+        vp, i = ctypes.c_void_p, ctypes.c_int
+        L.gvvo_backward.argtypes = [vp, i, vp, i, i, i, i, i, i, i, i, i, i] + [vp] * 12 + [vp] * 4 + [i]
+        L.gvvo_backward.restype = i
+        _lib64 = L
+    return _lib64
 
 
 def set_texture_bilinear(on):
@@ -96,20 +115,22 @@ def normal_map(faces, texcoords, N, C, vertex_pos, tex_h, tex_w):
 
 
 def backward(faces, texcoords, N, C, W, H, albedo, shading, image_filter, render_grad, target_grad, vertex_pos,
-             vertex_color, texture, sh_coeff, target_image, vertex_normal, bary, face, extrinsics, intrinsics, nthreads=0):
-    """Returns (vertex_pos_grad, vertex_color_grad, texture_grad, sh_coeff_grad)."""
+             vertex_color, texture, sh_coeff, target_image, vertex_normal, bary, face, extrinsics, intrinsics, nthreads=0, fp64=False):
+    """Returns (vertex_pos_grad, vertex_color_grad, texture_grad, sh_coeff_grad).
+    fp64: evaluate the same formulas at the same (fp32-valued) inputs in double precision and return float64 arrays."""
+    ft = np.float64 if fp64 else np.float32
     f = _c(np.asarray(faces).reshape(-1), np.int32)
-    t = _c(np.asarray(texcoords).reshape(-1), np.float32)
+    t = _c(np.asarray(texcoords).reshape(-1), ft)
     F = f.size // 3
-    rg, tg, vp_, vc_, tx_, sh_, ti_, vn_, ba_, ex_, in_ = (_c(a, np.float32) for a in (
+    rg, tg, vp_, vc_, tx_, sh_, ti_, vn_, ba_, ex_, in_ = (_c(a, ft) for a in (
         render_grad, target_grad, vertex_pos, vertex_color, texture, sh_coeff, target_image, vertex_normal, bary, extrinsics, intrinsics))
     fb = _c(face, np.int32)
     B, texH, texW = tx_.shape[0], tx_.shape[1], tx_.shape[2]
-    gpos = np.zeros((B, N, 3), np.float32)
-    gcol = np.zeros((B, N, 3), np.float32)
-    gtex = np.zeros((B, texH, texW, 3), np.float32)
-    gsh = np.zeros((B, C, 27), np.float32)
-    rc = _load().gvvo_backward(_p(f), F, _p(t), N, C, W, H, ALBEDO[albedo], SHADING[shading], image_filter, B, texH, texW,
+    gpos = np.zeros((B, N, 3), ft)
+    gcol = np.zeros((B, N, 3), ft)
+    gtex = np.zeros((B, texH, texW, 3), ft)
+    gsh = np.zeros((B, C, 27), ft)
+    rc = (_load64() if fp64 else _load()).gvvo_backward(_p(f), F, _p(t), N, C, W, H, ALBEDO[albedo], SHADING[shading], image_filter, B, texH, texW,
                                _p(rg), _p(tg), _p(vp_), _p(vc_), _p(tx_), _p(sh_), _p(ti_), _p(vn_), _p(ba_), _p(fb),
                                _p(ex_), _p(in_), _p(gpos), _p(gcol), _p(gtex), _p(gsh), nthreads)
     if rc:

@@ -25,6 +25,15 @@
 #include <omp.h>
 #endif
 
+// GVVO_FP64 build (oracle/libgvv_oracle64.so): the SAME source with every `float` -- arithmetic AND the I/O arrays --
+// turned into `double` after the standard headers have been parsed.  It evaluates the reference's formulas at the
+// same inputs without fp32 rounding and is what the gradient protocol uses to tell a genuine difference from the
+// reference's own fp32 noise (the position gradient's dJBCDVerpos chain, RendererUtil.h:670-861, subtracts terms
+// ~1e5 times larger than their difference when triangles are millimetres wide and the camera metres away).
+#ifdef GVVO_FP64
+#define float double
+#endif
+
 namespace {
 
 struct V3 { float x, y, z; };

@@ -3,8 +3,10 @@
   smooth_image    python/utils/GaussianSmoothingGpu.py:12-37 (tf.nn.depthwise_conv2d, SAME padding, 2-D kernel
                   outer(vals, vals) / sum) -- evaluated here literally as a 2-D cross-correlation, NOT separably
   image_gradient  imageGradient, cpp/src/Utils/RendererUtil.h:566-620, at every integer pixel
-Parity unpinned against the reference for smooth_image (TensorFlow is not installable here); image_gradient is
-the same code path the pinned backward oracle (gvv_oracle.cpp) uses for its model-to-data term.
+smooth_image is pinned by tests/golden/helpers/smooth_image.npz, a fixture produced by an independent restatement of the
+reference function on library primitives (tools/make_smooth_golden.py: torch.distributions.Normal + conv2d in fp64;
+TensorFlow itself is not installable here); image_gradient is the same code path the pinned backward oracle
+(gvv_oracle.cpp) uses for its model-to-data term.
 """
 import math
 

@@ -50,6 +50,7 @@ def _desc(**kw):
     (dict(shading_mode=2), "INVALID SHADING MODE"),
     (dict(albedo_mode=1), "textured albedo needs texture_coordinates"),
     (dict(num_vertices=2), "references vertex"),
+    (dict(width=8000, height=8000), "more than 40960 tiles"),          # rejected at create, not at the first launch
 ])
 def test_create_rejects_bad_attributes(kw, msg):
     L = _native.lib()
@@ -65,6 +66,7 @@ def test_null_handle_calls_fail_cleanly():
     assert L.gvv_forward(None, 1, 1, 1, *([None] * 14)) == 1
     assert L.gvv_backward(None, 1, 1, 1, *([None] * 17)) == 1
     assert L.gvv_destroy(None) == 0
+    assert L.gvv_reserve(None, 1, None) == 1
     assert L.gvv_launch_count(None) == 0
     out = ctypes.c_double()
     assert L.gvv_bench_atomics(0, 5, 1, 1, 1, ctypes.byref(out)) == 1

@@ -29,3 +29,14 @@ def test_image_gradient_of_a_ramp():
     # sum_x x*G_u = 2 (x=+-1,y=0) + 4*0.5 (corners) = 4 -> /4 = 1 per unit slope
     assert np.allclose(du[2:-2, 2:-2], 2.0, atol=1e-5) and np.allclose(dv[2:-2, 2:-2], 3.0, atol=1e-5)
     assert np.all(du[:2] == 0) and np.all(du[:, :2] == 0) and np.all(du[-2:] == 0) and np.all(du[:, -2:] == 0)
+
+
+def test_smooth_image_oracle_is_pinned_by_the_golden_fixture():
+    """tests/golden/helpers/smooth_image.npz: smoothImage (python/utils/GaussianSmoothingGpu.py:12-37) restated with
+    torch.distributions.Normal + torch.nn.functional.conv2d in fp64 by tools/make_smooth_golden.py (an independent
+    implementation of tfp Normal.prob / tf.nn.depthwise_conv2d SAME); pins oracle/helpers.smooth_image."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "helpers", "smooth_image.npz"))
+    for i, (size, mean, std) in enumerate(g["cases"]):
+        out = helpers.smooth_image(g["image"], int(size), float(mean), float(std))
+        assert np.abs(out - g[f"smoothed_{i}"]).max() <= 2e-7, (i, np.abs(out - g[f"smoothed_{i}"]).max())

@@ -23,6 +23,17 @@ def test_smooth_image_matches_numpy(size, mean, std):
     assert torch.equal(same, torch.as_tensor(img, device=DEV))       # size 0 / std 0 return the input (reference :14-15)
 
 
+def test_smooth_image_matches_the_golden_fixture():
+    """tests/golden/helpers/smooth_image.npz (tools/make_smooth_golden.py: the reference's smoothImage restated with
+    torch.distributions.Normal + conv2d in fp64) -- pins the CUDA helper, tolerance 2e-6 on [0,1) data."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "helpers", "smooth_image.npz"))
+    x = torch.as_tensor(g["image"], device=DEV)
+    for i, (size, mean, std) in enumerate(g["cases"]):
+        out = GaussianSmoothingGpu.smoothImage(x, int(size), float(mean), float(std))
+        assert np.abs(out.cpu().numpy() - g[f"smoothed_{i}"]).max() <= 2e-6
+
+
 def test_smooth_image_gradient_is_the_adjoint():
     g = torch.Generator().manual_seed(0)
     x = torch.randn((1, 2, 20, 24, 3), generator=g).to(DEV).requires_grad_(True)

@@ -176,3 +176,74 @@ def test_layer_step_is_cuda_graph_capturable_through_autograd():
         for a, b in zip(grads_s, grads_e):
             assert float((a - b).norm()) <= 1e-4 * float(b.norm()) + 1e-6
     del graph
+
+
+def test_handle_cache_eviction_keeps_live_handles_usable():
+    """More distinct attribute sets than the cache holds (16): the evicted handle must stay alive while a layer or a
+    pending autograd graph still uses it -- eviction only drops the cache's reference."""
+    from gvv_differentiable_cuda_renderer_b200 import CudaRenderer as mod
+    sc, t = scene(kind="sphere", rings=8, segments=10, cameras=1, width=40, height=40)
+    col = t["vertex_color"].clone().requires_grad_(True)
+    first = layer(sc, t, "vertexColor", "shaded", vertexColor_input=col)
+    h0 = first._handle
+    loss = first.getRenderBufferTF().sum()                  # graph outstanding across the evictions below
+    for k in range(mod._HANDLE_CACHE_MAX + 3):              # a resolution pyramid: a new handle per size
+        sc2, t2 = scene(kind="sphere", rings=8, segments=10, cameras=1, width=41 + k, height=40)
+        layer(sc2, t2, "vertexColor", "shaded")
+    assert len(mod._HANDLE_CACHE) <= mod._HANDLE_CACHE_MAX and all(h is not h0 for h in mod._HANDLE_CACHE.values())
+    assert h0._h                                            # evicted from the cache, not destroyed
+    loss.backward()
+    assert float(col.grad.abs().max()) > 0
+
+
+def test_device_without_index_and_argument_validation():
+    """device='cuda' means the current device; wrong dtypes / sizes raise instead of reading out of bounds."""
+    from gvv_differentiable_cuda_renderer_b200 import _native
+    sc, t = scene(kind="sphere", rings=8, segments=10, cameras=1, width=48, height=32)
+    r = layer(sc, t, "vertexColor", "shaded", device="cuda")
+    assert r.getRenderBufferTF().device == torch.device("cuda", torch.cuda.current_device())
+    nr = _native.NativeRenderer(sc["faces"], sc["texcoords"], sc["num_vertices"], 1, 48, 32, "vertexColor", "shaded", device="cuda")
+    ins = [t[k] for k in ("vertex_pos", "vertex_color", "texture", "sh_coeff", "target_image", "extrinsics", "intrinsics")]
+    bary, face, render, vn, _, _ = nr.forward(*ins)
+    g = torch.ones_like(render)
+    with pytest.raises(_native.GvvError, match="int32"):
+        nr.backward(g, None, ins[0], ins[1], ins[2], ins[3], ins[4], vn, bary, face.long(), ins[5], ins[6])
+    with pytest.raises(_native.GvvError, match="render_buffer_grad"):
+        nr.backward(g[..., :2].contiguous(), None, ins[0], ins[1], ins[2], ins[3], ins[4], vn, bary, face, ins[5], ins[6])
+    with pytest.raises(_native.GvvError, match="vertex_color"):
+        nr.forward(ins[0], ins[1][:, :-1].contiguous(), *ins[2:])
+    with pytest.raises(_native.GvvError, match="CUDA device"):
+        _native.NativeRenderer(sc["faces"], sc["texcoords"], sc["num_vertices"], 1, 48, 32, "vertexColor", "shaded", device="cpu")
+    nr.close()
+
+
+def test_scratch_growth_is_refused_once_graphs_hold_its_pointers():
+    """gvv_reserve sizes the scratch before capture; growing it afterwards would free memory that captured graphs
+    still use, so the call is refused with an error instead."""
+    from gvv_differentiable_cuda_renderer_b200 import _native
+    sc1, t1 = scene(kind="sphere", rings=10, segments=12, cameras=2, width=64, height=48, batch=1)
+    sc3, t3 = scene(kind="sphere", rings=10, segments=12, cameras=2, width=64, height=48, batch=3)
+    keys = ("vertex_pos", "vertex_color", "texture", "sh_coeff", "target_image", "extrinsics", "intrinsics")
+    nr = _native.NativeRenderer(sc1["faces"], sc1["texcoords"], sc1["num_vertices"], 2, 64, 48, "vertexColor", "shaded")
+    nr.reserve(2)
+    ins1 = [t1[k] for k in keys]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        nr.forward(*ins1)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = nr.forward(*ins1)
+    graph.replay()
+    torch.cuda.synchronize()
+    eager = nr.forward(*ins1)
+    assert torch.equal(out[1], eager[1])
+    with pytest.raises(_native.GvvError, match="captured"):
+        nr.forward(*[t3[k] for k in keys])                    # batch 3 > reserved 2: refused, the graph's scratch stays valid
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out[1], eager[1])
+    del graph
+    nr.close()
