@@ -64,10 +64,11 @@ class _CudaRendererFn(torch.autograd.Function):
     """cuda_renderer_gpu / cuda_renderer_grad_gpu (CudaRenderer.cpp:5-33, CudaRendererGrad.cpp:6-39)."""
 
     @staticmethod
-    def forward(ctx, handle, vertex_pos, vertex_color, texture, sh_coeff, target_image, extrinsics, intrinsics):
+    def forward(ctx, handle, shared, vertex_pos, vertex_color, texture, sh_coeff, target_image, extrinsics, intrinsics):
         bary, face, render, vnormal, target_out, normal_map = handle.forward(
             vertex_pos, vertex_color, texture, sh_coeff, target_image, extrinsics, intrinsics)
         ctx.handle = handle
+        ctx.shared = shared
         ctx.save_for_backward(vertex_pos, vertex_color, texture, sh_coeff, target_image, extrinsics, intrinsics,
                               bary, face, vnormal)
         ctx.mark_non_differentiable(face)
@@ -86,17 +87,30 @@ class _CudaRendererFn(torch.autograd.Function):
         else:
             if g_render is None:
                 g_render = torch.zeros_like(target_image)
-            gpos, gcol, gtex, gsh = handle.backward(g_render, g_target, vertex_pos, vertex_color, texture, sh_coeff,
-                                                    target_image, vnormal, bary, face, extrinsics, intrinsics)
+            shared = ctx.shared
+            out = None
+            if shared is not None:
+                # multi-GPU: the named gradients are written into the symmetric buffer's slot and summed across ranks
+                # by the backward itself (sharding.SharedGrads); autograd receives the sums
+                out = shared.outputs()
+                shared.buffer.attach(handle, shared.slot)
+            try:
+                gpos, gcol, gtex, gsh = handle.backward(g_render, g_target, vertex_pos, vertex_color, texture, sh_coeff,
+                                                        target_image, vnormal, bary, face, extrinsics, intrinsics, out=out)
+            finally:
+                if shared is not None:
+                    handle.set_allreduce(None)
+            if shared is not None:
+                gpos, gcol, gtex, gsh = shared.reduced((gpos, gcol, gtex, gsh))
             gpos, gcol, gtex, gsh = (g.view_as(t) for g, t in ((gpos, vertex_pos), (gcol, vertex_color),
                                                               (gtex, texture), (gsh, sh_coeff)))
         need = ctx.needs_input_grad
         # target image, extrinsics, intrinsics always get zeros (CudaRenderer.py:215)
-        return (None,
-                gpos if need[1] else None, gcol if need[2] else None, gtex if need[3] else None, gsh if need[4] else None,
-                torch.zeros_like(target_image) if need[5] else None,
-                torch.zeros_like(extrinsics) if need[6] else None,
-                torch.zeros_like(intrinsics) if need[7] else None)
+        return (None, None,
+                gpos if need[2] else None, gcol if need[3] else None, gtex if need[4] else None, gsh if need[5] else None,
+                torch.zeros_like(target_image) if need[6] else None,
+                torch.zeros_like(extrinsics) if need[7] else None,
+                torch.zeros_like(intrinsics) if need[8] else None)
 
 
 def _as_cuda(x, device, name):
@@ -135,7 +149,8 @@ class CudaRendererGpu:
 
                  nodeName='CudaRenderer',
                  device=None,
-                 textureBilinear_attr=False):
+                 textureBilinear_attr=False,
+                 sharedGrads_attr=None):
         self.faces_attr = faces_attr
         self.texCoords_attr = texCoords_attr
         self.numberOfVertices_attr = numberOfVertices_attr
@@ -151,6 +166,9 @@ class CudaRendererGpu:
         # extension (not in the reference signature, default = reference behaviour): bilinear texture fetch and
         # weighted 4-texel texture-gradient scatter, the variants the reference has commented out
         self.textureBilinear_attr = bool(textureBilinear_attr)
+        # extension for the sharded (one process per GPU) path: a sharding.SharedGrads -- the gradients it names come
+        # back from autograd already summed over the ranks (one-shot all-reduce inside the backward's last kernel)
+        self.sharedGrads_attr = sharedGrads_attr
 
         if device is None:
             device = vertexPos_input.device if isinstance(vertexPos_input, torch.Tensor) and vertexPos_input.is_cuda \
@@ -168,7 +186,7 @@ class CudaRendererGpu:
                                    renderResolutionU_attr, renderResolutionV_attr, albedoMode_attr, shadingMode_attr,
                                    image_filter_size_attr, texture_filter_size_attr, compute_normal_map_attr, self.device,
                                    self.textureBilinear_attr)
-        self.cudaRendererOperator = _CudaRendererFn.apply(self._handle, self.vertexPos_input, self.vertexColor_input,
+        self.cudaRendererOperator = _CudaRendererFn.apply(self._handle, self.sharedGrads_attr, self.vertexPos_input, self.vertexColor_input,
                                                           self.texture_input, self.shCoeff_input, self.targetImage_input,
                                                           self.extrinsics_input, self.intrinsics_input)
 

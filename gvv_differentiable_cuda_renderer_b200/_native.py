@@ -48,13 +48,20 @@ class gvv_desc(ctypes.Structure):
                 ("compute_normal_map", ctypes.c_int32), ("device", ctypes.c_int32)]
 
 
+class gvv_allreduce_desc(ctypes.Structure):
+    _fields_ = [("peer_buffers", ctypes.c_void_p), ("signal_pads", ctypes.c_void_p), ("multicast_ptr", ctypes.c_uint64),
+                ("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("offset_floats", ctypes.c_int64), ("count_floats", ctypes.c_int64),
+                ("result", ctypes.c_void_p), ("mode", ctypes.c_int32), ("channels", ctypes.c_int32), ("first_channel", ctypes.c_int32),
+                ("after_backward", ctypes.c_int32)]
+
+
 _lib = None
 
 # every symbol include/gvv_b200.h declares
 EXPORTS = ["gvv_create", "gvv_destroy", "gvv_reserve", "gvv_forward", "gvv_backward", "gvv_last_error", "gvv_launch_count",
            "gvv_debug_copy", "gvv_debug_eval", "gvv_set_option", "gvv_bench_atomics",
            "gvv_kernel_count", "gvv_kernel_name", "gvv_kernel_times",
-           "gvv_gaussian_smooth", "gvv_image_gradient", "gvv_set_target_gradient"]
+           "gvv_gaussian_smooth", "gvv_image_gradient", "gvv_set_target_gradient", "gvv_set_allreduce"]
 
 
 def lib():
@@ -95,6 +102,8 @@ def lib():
         L.gvv_gaussian_smooth.restype = ctypes.c_int
         L.gvv_image_gradient.argtypes = [i32, i64, i32, i32, i32, vp, vp, vp, vp]
         L.gvv_image_gradient.restype = ctypes.c_int
+        L.gvv_set_allreduce.argtypes = [vp, ctypes.POINTER(gvv_allreduce_desc)]
+        L.gvv_set_allreduce.restype = ctypes.c_int
         L.gvv_set_target_gradient.argtypes = [vp, vp, vp]
         L.gvv_set_target_gradient.restype = ctypes.c_int
         _lib = L
@@ -208,6 +217,8 @@ class NativeRenderer:
 
     def set_option(self, key, value):
         _check(lib().gvv_set_option(self._h, key.encode(), int(value)), "gvv_set_option")
+        if key == "shared_batch_grads":
+            self.shared_batch_grads = bool(value)
 
     @property
     def launch_count(self):
@@ -290,7 +301,8 @@ class NativeRenderer:
         o = dict(device=dev, dtype=torch.float32)
         with _device_ctx(dev):
             pre = tuple(out) if out is not None else (None, None, None, None)
-            shapes = ((B, N, 3), (B, N, 3), (B, texH, texW, 3), (B, C, 27))
+            Bs = 1 if getattr(self, "shared_batch_grads", False) else B     # set_option("shared_batch_grads", 1)
+            shapes = ((B, N, 3), (Bs, N, 3), (Bs, texH, texW, 3), (Bs, C, 27))
             outs = []
             for t, shp, name in zip(pre, shapes, ("vertex_pos_grad", "vertex_color_grad", "texture_grad", "sh_coeff_grad")):
                 if t is None:
@@ -303,6 +315,10 @@ class NativeRenderer:
                                       _ptr(extrinsics), _ptr(intrinsics), _ptr(gpos), _ptr(gcol), _ptr(gtex),
                                       _ptr(gsh), self._stream()), "gvv_backward")
         return gpos, gcol, gtex, gsh
+
+    def set_allreduce(self, desc):
+        """desc: gvv_allreduce_desc or None -- the one-shot all-reduce gvv_backward ends with (sharding.SymmetricGradBuffer)."""
+        _check(lib().gvv_set_allreduce(self._h, ctypes.byref(desc) if desc is not None else None), "gvv_set_allreduce")
 
     def set_target_gradient(self, d_du, d_dv):
         """Hand the precomputed target-image gradient (image_gradient(target, image_filter_size)) to the

@@ -251,6 +251,7 @@ extern "C" int gvv_set_option(gvv_handle h, const char* key, int32_t value) {
   if (!strcmp(key, "cta_threads")) { if (value != 128 && value != 256) return fail(GVV_EINVAL, "cta_threads must be 128 or 256"); h->ctaThreads = value; return GVV_OK; }
   if (!strcmp(key, "span_z")) { if (value < 0 || value > 2) return fail(GVV_EINVAL, "span_z must be 0 (off), 1 (both passes) or 2 (far pass only)"); h->spanZ = value; return GVV_OK; }
   if (!strcmp(key, "cta_trace")) { if (h->captured) return fail(GVV_EINVAL, "cta_trace cannot change after the handle was used under stream capture"); cudaSetDevice(h->device); cudaDeviceSynchronize(); free_scratch(h->s); h->ctaTrace = value ? 1 : 0; return GVV_OK; }   // scratch is re-allocated by the next call
+  if (!strcmp(key, "shared_batch_grads")) { h->sharedBatchGrads = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "texture_bilinear")) { h->texBilinear = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "chain")) { h->chain = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "resolve_prefetch")) { h->resolvePrefetch = value ? 1 : 0; return GVV_OK; }
@@ -365,16 +366,37 @@ extern "C" int gvv_backward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
 
   BwdArgs a;
   a.B = B; a.C = h->C; a.N = h->N; a.F = h->F; a.W = h->W; a.H = h->H; a.texH = texH; a.texW = texW;
-  a.albedo = h->albedo; a.shading = h->shading; a.imgFilter = h->imgFilter; a.texBilinear = h->texBilinear; a.chain = h->chain && !h->timer.enabled; a.target_du = h->targetDu; a.target_dv = h->targetDv;
+  a.albedo = h->albedo; a.shading = h->shading; a.imgFilter = h->imgFilter; a.texBilinear = h->texBilinear; a.chain = h->chain && !h->timer.enabled; a.sharedBatch = h->sharedBatchGrads; a.target_du = h->targetDu; a.target_dv = h->targetDv;
   a.render_grad = render_grad; a.target_grad = target_grad; a.vertex_pos = vertex_pos; a.vertex_color = vertex_color;
   a.texture = texture; a.sh_coeff = sh_coeff; a.target_image = target_image; a.vertex_normal = vertex_normal;
   a.bary = bary; a.extrinsics = extrinsics; a.intrinsics = intrinsics; a.texcoords = h->texcoords;
   a.face = face; a.faces4 = h->faces4; a.vfOffsets = h->vfOffsets; a.vfList = h->vfList;
   a.vpos_grad = vpos_grad; a.vcol_grad = vcol_grad; a.tex_grad = tex_grad; a.sh_grad = sh_grad;
+  a.ar = h->ar; a.arAfter = h->arAfter;
   a.s = h->s;
   const int n = launch_backward(a, st, &h->timer);
   if (n < 0) return fail(GVV_ECUDA, "backward launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   h->launches += n;
+  return GVV_OK;
+}
+
+extern "C" int gvv_set_allreduce(gvv_handle h, const gvv_allreduce_desc* d) {
+  if (!h) return fail(GVV_EINVAL, "gvv_set_allreduce: null handle");
+  if (!d) { h->ar = ARParams{}; h->arAfter = 0; return GVV_OK; }
+  if (d->world < 1 || d->world > kMaxWorld || d->rank < 0 || d->rank >= d->world) return fail(GVV_EINVAL, "gvv_set_allreduce: bad rank / world (at most %d ranks)", kMaxWorld);
+  if (!d->peer_buffers || !d->signal_pads || !d->result) return fail(GVV_EINVAL, "gvv_set_allreduce: null pointer");
+  if (d->count_floats <= 0 || d->offset_floats < 0 || (d->offset_floats & 3)) return fail(GVV_EINVAL, "gvv_set_allreduce: the range must be non-empty and start at a multiple of 4 floats");
+  if (reinterpret_cast<uintptr_t>(d->result) & 15) return fail(GVV_EINVAL, "gvv_set_allreduce: result must be 16-byte aligned");
+  if (d->mode != 0 && d->mode != 1) return fail(GVV_EINVAL, "gvv_set_allreduce: mode must be 0 (peer loads) or 1 (NVLS multimem.ld_reduce)");
+  if (d->mode == 1 && (!d->multicast_ptr || (d->count_floats & 3))) return fail(GVV_EINVAL, "gvv_set_allreduce: NVLS mode needs a multicast mapping and a count that is a multiple of 4");
+  if (d->channels < 1 || d->channels > 64 || d->first_channel < 0) return fail(GVV_EINVAL, "gvv_set_allreduce: channels must be in [1,64]");
+  ARParams a;
+  a.peers = reinterpret_cast<const float* const*>(d->peer_buffers);
+  a.pads = reinterpret_cast<uint32_t* const*>(d->signal_pads);
+  a.mc = reinterpret_cast<const float*>(d->multicast_ptr);
+  a.result = d->result; a.offset = d->offset_floats; a.count = d->count_floats;
+  a.rank = d->rank; a.world = d->world; a.mode = d->mode; a.blocks = d->channels; a.channelBase = d->first_channel;
+  h->ar = a; h->arAfter = d->after_backward ? 1 : 0;
   return GVV_OK;
 }
 
@@ -429,7 +451,7 @@ extern "C" int gvv_debug_eval(gvv_handle h, int32_t n, const int32_t* queries, i
 
 static const char* kKernelNames[K_NUM_SLOTS] = {"camera_kernel", "vertex_kernel", "bin_count_kernel", "bin_scan_kernel",
                                                 "bin_fill_kernel", "raster_kernel", "prep_kernel", "pixel_grad_kernel",
-                                                "normal_term_kernel", "normal_map_kernel"};
+                                                "normal_term_kernel", "normal_map_kernel", "allreduce_kernel"};
 
 extern "C" int32_t gvv_kernel_count(void) { return K_NUM_SLOTS; }
 extern "C" const char* gvv_kernel_name(int32_t i) { return (i >= 0 && i < K_NUM_SLOTS) ? kKernelNames[i] : ""; }

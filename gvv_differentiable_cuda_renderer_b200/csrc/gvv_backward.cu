@@ -45,6 +45,7 @@ struct PixelParams {
   const float4 *pos4, *col4, *nor4;
   float *vpos_grad, *vcol_grad, *tex_grad, *sh_grad, *gnorm;
   int C, N, W, H, texH, texW, albedo, shading, imgFilter, texBilinear;
+  int sharedBatch;   // 1: colour / texture / SH gradients of every batch element accumulate into ONE slice (parameters shared across the batch)
   float invC;
 };
 
@@ -219,7 +220,7 @@ pixel_grad_kernel(const PixelParams p) {
           alb[ch] = (v - LV) * ((u - LU) * cLULV + (HU - u) * cHULV) + (HV - v) * ((u - LU) * cLUHV + (HU - u) * cHUHV);
         }
         if (!flipped) {
-          float* tgb = p.tex_grad + (size_t)b * p.texH * p.texW * 3;
+          float* tgb = p.tex_grad + (size_t)(p.sharedBatch ? 0 : b) * p.texH * p.texW * 3;
           if (p.texBilinear) {
             // non-default variant: the four weighted adds the reference has commented out (:361-378), weights as written there
             const float wLULV = (v - LV) * (u - LU), wLUHV = (HV - v) * (u - LU), wHULV = (v - LV) * (HU - u), wHUHV = (HV - v) * (HU - u);
@@ -335,7 +336,7 @@ pixel_grad_kernel(const PixelParams p) {
                                          (arr == 1 && (shaded || p.target_grad)) || (arr == 2 && shaded));
     float* base = arr == 0 ? p.vcol_grad : (arr == 1 ? p.vpos_grad : p.gnorm);
     const int vstride = arr == 2 ? 4 : 3;          // gnorm is float4-strided for aligned gathers in normal_term_kernel
-    base += (size_t)b * p.N * vstride + comp;
+    base += (size_t)((arr == 0 && p.sharedBatch) ? 0 : b) * p.N * vstride + comp;
     // Lane j walks row j (the 32 pixels' value j) with a segmented running sum: flushed with ONE
     // warp-wide atomic at the end of every run of equal face id and reset to zero there (pixels outside
     // a run hold zeros).  endm is warp-uniform, so the 32 steps are unrolled with uniform branches.
@@ -390,7 +391,7 @@ pixel_grad_kernel(const PixelParams p) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += shPart[w][tid];
-    if (s != 0.f) atomicAdd(p.sh_grad + (size_t)view * 27 + tid, s);
+    if (s != 0.f) atomicAdd(p.sh_grad + (size_t)(p.sharedBatch ? view - b * p.C : view) * 27 + tid, s);
   }
 }
 
@@ -438,11 +439,19 @@ __global__ void prep_kernel(PrepArgs a) {
 // the three cross-product Jacobians (getJ_vi/vj/vk, RendererUtil.h:422-539) scattered to its vertices.
 // Triangles none of whose vertices received a normal gradient (about 2/3 of them: back faces,
 // occluded parts) leave after three 16-byte loads.
+// The first ar.blocks CTAs (of batch element 0) do not touch triangles: they run the one-shot all-reduce of the
+// shared-parameter gradients over peer memory (gvv_collective.cuh) while the others compute -- SH and colour gradients
+// are final once pixel_grad_kernel has ended, this kernel only adds to vertex_pos_grad.
 __global__ void __launch_bounds__(256)
 normal_term_kernel(const float4* __restrict__ pos4, const float4* __restrict__ gnorm4, const int4* __restrict__ faces4,
-                   float* __restrict__ vpos_grad, int N, int F) {
+                   float* __restrict__ vpos_grad, int N, int F, const ARParams ar) {
   chain_wait(); chain_trigger();
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  int bx = blockIdx.x;
+  if (blockIdx.y == 0) {
+    if (bx < ar.blocks) { allreduce_block(ar, bx); return; }
+    bx -= ar.blocks;
+  }
+  const int f = bx * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (f >= F) return;
   const int4 fc = __ldg(faces4 + f);
@@ -463,6 +472,13 @@ normal_term_kernel(const float4* __restrict__ pos4, const float4* __restrict__ g
   atomicAdd(out + 3 * (size_t)fc.z, gk.x); atomicAdd(out + 3 * (size_t)fc.z + 1, gk.y); atomicAdd(out + 3 * (size_t)fc.z + 2, gk.z);
 }
 
+// the same all-reduce as a launch of its own: ranges that include vertex_pos_grad (cameras of one batch element split
+// over ranks) are only final after normal_term_kernel
+__global__ void __launch_bounds__(256) allreduce_kernel(const ARParams ar) {
+  chain_wait(); chain_trigger();
+  allreduce_block(ar, blockIdx.x);
+}
+
 // ------------------------------------------------------------------------------------------------
 int launch_camera(const float* extr, const float* intr, CamRec* cams, int* bigCount, int V, cudaStream_t st);
 
@@ -472,10 +488,11 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   ZeroArgs z;
   const long long nv = (long long)a.B * a.N * 3;
   z.p[0] = a.vpos_grad; z.n[0] = nv;
-  z.p[1] = a.vcol_grad; z.n[1] = nv;
+  const long long Bs = a.sharedBatch ? 1 : a.B;        // batch extent of the colour / texture / SH gradients
+  z.p[1] = a.vcol_grad; z.n[1] = Bs * a.N * 3;
   z.p[2] = a.s.gnorm;   z.n[2] = (long long)a.B * a.N * 4;
-  z.p[3] = a.sh_grad;   z.n[3] = (long long)V * 27;
-  z.p[4] = a.tex_grad;  z.n[4] = a.tex_grad ? (long long)a.B * a.texH * a.texW * 3 : 0;
+  z.p[3] = a.sh_grad;   z.n[3] = Bs * a.C * 27;
+  z.p[4] = a.tex_grad;  z.n[4] = a.tex_grad ? Bs * a.texH * a.texW * 3 : 0;
   PrepArgs pa;
   pa.z = z;
   pa.vertex_pos = a.vertex_pos; pa.vertex_color = a.vertex_color; pa.vertex_normal = a.vertex_normal;
@@ -493,7 +510,7 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   p.pos4 = a.s.bpos4; p.col4 = a.s.bcol4; p.nor4 = a.s.bnor4;
   p.vpos_grad = a.vpos_grad; p.vcol_grad = a.vcol_grad; p.tex_grad = a.tex_grad; p.sh_grad = a.sh_grad; p.gnorm = a.s.gnorm;
   p.C = a.C; p.N = a.N; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
-  p.albedo = a.albedo; p.shading = a.shading; p.imgFilter = a.imgFilter; p.texBilinear = a.texBilinear; p.invC = 1.f / (float)a.C;
+  p.albedo = a.albedo; p.shading = a.shading; p.imgFilter = a.imgFilter; p.texBilinear = a.texBilinear; p.sharedBatch = a.sharedBatch; p.invC = 1.f / (float)a.C;
   tm->begin(K_PIXEL_GRAD, st);
   constexpr int kPixelSmem = 8 * kWarpBufFloats * (int)sizeof(float);
   const dim3 pgGrid((a.W + 31) / 32, (a.H + 31) / 32, V);
@@ -507,10 +524,20 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
 #undef GVV_PG
   tm->end(st);
   ++launches;
-  if (a.shading == GVV_SHADING_SHADED) {
+  const bool fusedAR = a.ar.blocks > 0 && !a.arAfter;
+  if (a.shading == GVV_SHADING_SHADED || fusedAR) {
+    ARParams ar = a.ar;
+    if (!fusedAR) ar.blocks = 0;
+    const int Fn = a.shading == GVV_SHADING_SHADED ? a.F : 0;         // shadeless: the kernel only carries the collective
     tm->begin(K_NORMAL_TERM, st);
-    launch_chained(a.chain, normal_term_kernel, dim3((a.F + 255) / 256, a.B), dim3(256), 0, st, a.s.bpos4, reinterpret_cast<const float4*>(a.s.gnorm), a.faces4,
-                   a.vpos_grad, a.N, a.F);
+    launch_chained(a.chain, normal_term_kernel, dim3((Fn + 255) / 256 + ar.blocks, Fn ? a.B : 1), dim3(256), 0, st, a.s.bpos4, reinterpret_cast<const float4*>(a.s.gnorm), a.faces4,
+                   a.vpos_grad, a.N, Fn, ar);
+    tm->end(st);
+    ++launches;
+  }
+  if (a.ar.blocks > 0 && a.arAfter) {
+    tm->begin(K_ALLREDUCE, st);
+    launch_chained(a.chain, allreduce_kernel, dim3(a.ar.blocks), dim3(256), 0, st, a.ar);
     tm->end(st);
     ++launches;
   }

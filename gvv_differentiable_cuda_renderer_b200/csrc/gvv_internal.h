@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "gvv_exact.cuh"
+#include "gvv_collective.cuh"
 #include "../../include/gvv_b200.h"
 
 namespace gvv {
@@ -42,7 +43,7 @@ struct Scratch {
 };
 
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py roofline leg).
-enum KernelSlot { K_CAMERA = 0, K_VERTEX, K_BIN_COUNT, K_BIN_SCAN, K_BIN_FILL, K_RASTER, K_ZERO, K_PIXEL_GRAD, K_NORMAL_TERM, K_NORMAL_MAP, K_NUM_SLOTS };
+enum KernelSlot { K_CAMERA = 0, K_VERTEX, K_BIN_COUNT, K_BIN_SCAN, K_BIN_FILL, K_RASTER, K_ZERO, K_PIXEL_GRAD, K_NORMAL_TERM, K_NORMAL_MAP, K_ALLREDUCE, K_NUM_SLOTS };
 
 struct KernelTimer {
   bool enabled = false;
@@ -69,6 +70,7 @@ struct gvv_renderer {
   int captured = 0;           // the handle has been used while its stream was being captured: the scratch pointers are baked into CUDA graphs
   int chain = 1;              // launch the kernels of a call as a programmatic dependent-launch chain
   int resolvePrefetch = 0;    // raster: L1 prefetch sweep of the resolve stage's vertex gathers (measured slower: 0.272 -> 0.282 ms)
+  int sharedBatchGrads = 0;   // backward: vertex_color / texture / sh_coeff gradients are summed over the batch into [1, ...] outputs (parameters shared across the batch)
   int texBilinear = 0;        // non-default: bilinear texture fetch + weighted 4-texel gradient scatter (the variants the reference has commented out)
   int spreadEmpty = 0;        // raster: interleave the (HBM-bound) empty tiles with the (ALU-bound) non-empty ones
   int heavyMode = 1;          // 0 = never, 1 = only where such a bin would be the critical path of the launch (decided on the GPU), 2 = always
@@ -92,6 +94,8 @@ struct gvv_renderer {
   int* vfList = nullptr;      // [vfOffsets[N]]
   // UV-space (face, a, b, c) table for compute_normal_map, built lazily per texture size
   float4* texelTable = nullptr; int tableH = 0, tableW = 0;
+  gvv::ARParams ar = {};     // one-shot all-reduce of shared-parameter gradients at the end of gvv_backward (gvv_set_allreduce); blocks == 0: none
+  int arAfter = 0;            // 1: the reduced range includes vertex_pos_grad -> own launch after the last kernel instead of CTAs inside it
   gvv::Scratch s;
   int64_t launches = 0;
   gvv::KernelTimer timer;
@@ -112,13 +116,14 @@ struct FwdArgs {
 };
 
 struct BwdArgs {
-  int B, C, N, F, W, H, texH, texW, albedo, shading, imgFilter, texBilinear, chain;
+  int B, C, N, F, W, H, texH, texW, albedo, shading, imgFilter, texBilinear, chain, sharedBatch;
   const float *render_grad, *target_grad, *vertex_pos, *vertex_color, *texture, *sh_coeff, *target_image,
       *vertex_normal, *bary, *extrinsics, *intrinsics, *texcoords, *target_du, *target_dv;
   const int32_t* face;
   const int4* faces4;
   const int *vfOffsets, *vfList;
   float *vpos_grad, *vcol_grad, *tex_grad, *sh_grad;
+  ARParams ar; int arAfter;
   Scratch s;
 };
 

@@ -128,6 +128,35 @@ int gvv_backward(gvv_handle h, int32_t batch, int32_t tex_h, int32_t tex_w,
 
 const char* gvv_last_error(void);
 
+/* ---- multi-GPU: one-shot all-reduce of shared-parameter gradients over peer memory ----------------------------
+ * The reference has no multi-GPU path (python/utils/CheckGPU.py:51-52 masks all but one GPU).  Views are
+ * sharded over one process per GPU; the only exchange is the sum of gradients of parameters several ranks share.
+ * With a descriptor set, gvv_backward ends by reducing the float range [offset_floats, offset_floats + count_floats)
+ * of every rank's SYMMETRIC buffer (each rank passes gradient output pointers inside its own buffer to gvv_backward)
+ * into `result` on every rank:  result[i] = sum over ranks r of peer_buffers[r][offset_floats + i], rank order 0..W-1.
+ *   peer_buffers   DEVICE array [world] of the base addresses, as mapped in THIS process, of every rank's buffer
+ *   signal_pads    DEVICE array [world] of uint32 signal pads (zero-initialised; words (first_channel + c) * world + r,
+ *                  c < channels, are used and left zero)
+ *   multicast_ptr  NVLS multicast mapping of the buffer (0 if none); mode 1 reads the sum from the switch
+ *   after_backward 0: the range holds only gradients that are final after the per-pixel kernel (SH, colours, texture):
+ *                  the exchange runs as `channels` CTAs INSIDE the backward's last kernel, overlapped with its math;
+ *                  1: the range includes vertex_pos_grad: a kernel of its own follows the backward
+ * The caller alternates between two ranges (slots) from step to step: a slot is rewritten two barriers after it was
+ * read.  NULL removes the descriptor.  Buffers, pads and the pointer arrays stay owned by the caller. */
+typedef struct gvv_allreduce_desc {
+  const void* peer_buffers;
+  const void* signal_pads;
+  uint64_t    multicast_ptr;
+  int32_t     rank, world;
+  int64_t     offset_floats, count_floats;
+  float*      result;
+  int32_t     mode;            /* 0 = peer loads over NVLink (ld.global.sys), 1 = NVLS multimem.ld_reduce */
+  int32_t     channels;        /* CTAs taking part, 1..64 */
+  int32_t     first_channel;
+  int32_t     after_backward;
+} gvv_allreduce_desc;
+int gvv_set_allreduce(gvv_handle h, const gvv_allreduce_desc* desc);
+
 /* ---- loss-side helpers next to the op; no handle needed ----------------- */
 
 /* smoothImage (python/utils/GaussianSmoothingGpu.py:12-37): depthwise Gaussian over `images` dense
@@ -167,7 +196,11 @@ int64_t gvv_debug_copy(gvv_handle h, int32_t which, void* host_dst, int64_t capa
  * fails the inside test; out_ab: HOST float[n*2] barycentrics (a,b).  Synchronises `stream`. */
 int gvv_debug_eval(gvv_handle h, int32_t n, const int32_t* queries, int32_t* out_key, float* out_ab, void* stream);
 
-/* Runtime knobs.  Behaviour: "texture_bilinear" (1: the bilinear texture fetch and the weighted 4-texel
+/* Runtime knobs.  Behaviour: "shared_batch_grads" (1: vertex_color_grad, texture_grad and sh_coeff_grad are accumulated
+ * over the batch into outputs of batch extent ONE -- [1,N,3], [1,texH,texW,3], [1,C,27] -- for parameters the caller
+ * shares across the batch, e.g. one template colour set / texture / illumination for all batch elements; the reference
+ * leaves that sum to the framework's autodiff of a broadcast; vertex_pos_grad stays per batch element; default 0),
+ * "texture_bilinear" (1: the bilinear texture fetch and the weighted 4-texel
  * texture-gradient scatter the reference has commented out, CUDABasedRasterization.cu:365-372,
  * CUDABasedRasterizationGrad.cu:361-378; default 0 = reference behaviour: nearest texel, unweighted add).
  * Scheduling / culling (results are bit-identical for every setting, see tests; defaults = measured best on a

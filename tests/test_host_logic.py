@@ -99,3 +99,78 @@ def test_gloo_world2_shared_grad_allreduce_and_gather(B):
         p.join(60)
         assert p.exitcode == 0
     assert sorted(r[0] for r in res) == [0, 1] and all(r[1] and r[2] for r in res)
+
+
+@pytest.mark.parametrize("B,C,W", [(1, 8, 8), (2, 16, 8), (1, 3, 4), (3, 5, 8), (8, 16, 8), (64, 16, 8), (1, 1, 2)])
+def test_plan_views_covers_every_view_exactly_once(B, C, W):
+    plan = sharding.plan_views(B, C, W)
+    assert len(plan) == W
+    seen = np.zeros((B, C), int)
+    for p in plan:
+        if p is not None:
+            b0, b1, c0, c1 = p
+            assert 0 <= b0 < b1 <= B and 0 <= c0 < c1 <= C
+            seen[b0:b1, c0:c1] += 1
+    assert (seen == 1).all()                                     # every (batch element, camera) rendered by exactly one rank
+    if B >= W:
+        assert sharding.camera_teams(plan) == []                 # whole batch elements per rank: no collective inside the op
+    else:
+        for team in sharding.camera_teams(plan):
+            assert len({plan[r][:2] for r in team}) == 1         # a team shares one batch element
+
+
+def _fake_backward(inp):
+    """Stand-in for the op's backward with its accumulation structure (CudaRendererGrad.cpp:264-283): position / colour /
+    texture gradients are SUMS over the cameras of a batch element, sh_coeff_grad has one row per (b, c)."""
+    w = inp["sh_coeff"].sum(-1)                                           # [b, c]: a per-view weight
+    e = inp["extrinsics"].reshape(inp["extrinsics"].shape[0], -1, 12).sum(-1) + inp["intrinsics"].reshape(inp["intrinsics"].shape[0], -1, 9).sum(-1)
+    per_view = w * e + inp["target_image"].sum((2, 3, 4))                # [b, c]
+    gpos = inp["vertex_pos"] * per_view.sum(1)[:, None, None]
+    gcol = inp["vertex_color"] * (per_view ** 2).sum(1)[:, None, None]
+    gtex = inp["texture"] * per_view.sum(1)[:, None, None, None]
+    gsh = inp["sh_coeff"] * per_view[:, :, None]
+    return gpos, gcol, gtex, gsh
+
+
+def _camera_split_worker(rank, world, port, B, C, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(5)
+        full = {"vertex_pos": torch.randn(B, 6, 3, generator=g), "vertex_color": torch.rand(B, 6, 3, generator=g),
+                "texture": torch.rand(B, 4, 4, 3, generator=g), "sh_coeff": torch.randn(B, C, 27, generator=g),
+                "target_image": torch.rand(B, C, 5, 7, 3, generator=g), "extrinsics": torch.randn(B, C * 12, generator=g),
+                "intrinsics": torch.randn(B, C * 9, generator=g)}
+        plan = sharding.plan_views(B, C, world)
+        groups = sharding.make_team_groups(plan)
+        mine = plan[rank]
+        want = _fake_backward(full)
+        ok = True
+        if mine is not None:
+            loc = sharding.shard_views(full, C, mine)
+            assert loc["sh_coeff"].shape == (mine[1] - mine[0], mine[3] - mine[2], 27)
+            assert loc["extrinsics"].shape == (mine[1] - mine[0], (mine[3] - mine[2]) * 12)
+            grads = sharding.reduce_camera_split(_fake_backward(loc), plan, C, rank=rank, groups=groups)
+            for got, ref in zip(grads, want):
+                ok = ok and torch.allclose(got, ref[mine[0]:mine[1]], rtol=1e-5, atol=1e-5)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B,C", [(1, 4), (1, 3), (2, 5)])
+def test_gloo_world2_camera_split_reduces_like_one_process(B, C):
+    """Cameras of one batch element split over two ranks: after reduce_camera_split every rank holds the gradients
+    a single process computes over all cameras (B >= world degenerates to the batch split, no collective)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_camera_split_worker, args=(r, 2, port, B, C, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1] and all(r[1] for r in res)
