@@ -33,11 +33,16 @@ _OUT = sys.stdout
 BASE = json.load(open(os.path.join(ROOT, "BASELINE.json"))) if os.path.exists(os.path.join(ROOT, "BASELINE.json")) else {}
 METRIC = BASE.get("metric", "views/sec fwd+bwd at 1024^2, 70k tris")
 UNIT = "views/s"
-WORKLOAD = dict(rings=187, segments=188, cameras=8, width=1024, height=1024, tex=64)
+WORKLOAD = dict(rings=187, segments=188, width=1024, height=1024, tex=64)
 INPUT_KEYS = ("vertex_pos", "vertex_color", "texture", "sh_coeff", "target_image", "extrinsics", "intrinsics")
 # the SAME string in both arms (the driver compares the two config objects)
 WORKLOAD_NAME = ("config2: UV-sphere 34970 verts / 69936 tris, 8 ring cameras, 1024x1024, ~52% coverage, vertexColor+shaded, "
                  "fwd+bwd (grads wrt positions, colours, SH), B=1 (8 views) per GPU per step")
+# per-GPU share of the named workload; config2 is the bench line, config4 (BASELINE.json: 64 x 16 cameras over 8 GPUs) a second one
+WORKLOADS = {"config2": dict(batch=1, cameras=8, name=WORKLOAD_NAME),
+             "config4": dict(batch=8, cameras=16, name="config4: multi-view capture batch, 64 batch elements x 16 cameras at 1024x1024 over 8 GPUs = B=8 x C=16 "
+                                                        "(128 views) per GPU per step, UV-sphere 34970 verts / 69936 tris, vertexColor+shaded, fwd+bwd, SH and "
+                                                        "colours shared across the batch (one summed gradient each, all-reduced over the GPUs)")}
 
 
 def peaks():
@@ -88,12 +93,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(rank):
+def make_inputs(rank, workload="config2"):
     from gvv_differentiable_cuda_renderer_b200 import synthetic
-    sc = synthetic.make_scene(kind="sphere", batch=1, seed=0, **WORKLOAD)
-    if rank:   # every rank renders its own batch element: same topology, different vertex noise
+    wl = WORKLOADS[workload]
+    sc = synthetic.make_scene(kind="sphere", batch=wl["batch"], cameras=wl["cameras"], seed=0, **WORKLOAD)
+    if rank:   # every rank renders its own batch elements: same topology, different vertex noise
         rng = np.random.default_rng(100 + rank)
         sc["vertex_pos"] = (sc["vertex_pos"] + rng.normal(0, 0.3, sc["vertex_pos"].shape)).astype(np.float32)
+    if wl["batch"] > 1:   # SH and colours are parameters SHARED across the batch: one set, expanded to the op's [B, ...] inputs
+        sc["vertex_color"] = np.ascontiguousarray(np.broadcast_to(sc["vertex_color"][:1], sc["vertex_color"].shape))
+        sc["sh_coeff"] = np.ascontiguousarray(np.broadcast_to(sc["sh_coeff"][:1], sc["sh_coeff"].shape))
     return sc
 
 
@@ -117,29 +126,60 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner must not land on stdout next to the JSON line
         dist.init_process_group("nccl", device_id=dev)
-    sc = make_inputs(rank)
+    wl = WORKLOADS[args.workload]
+    sc = make_inputs(rank, args.workload)
     N, C, W, H = sc["num_vertices"], sc["num_cameras"], sc["width"], sc["height"]
-    V = C   # views per step per GPU (B = 1)
+    B = wl["batch"]
+    V = B * C   # views per step per GPU
     ins = [torch.as_tensor(sc[k], device=dev) for k in INPUT_KEYS]
-    G = torch.randn((1, C, H, W, 3), generator=torch.Generator().manual_seed(3)).to(dev)   # render_buffer_grad ~ N(0,1) seed 3
+    G = torch.randn((B, C, H, W, 3), generator=torch.Generator().manual_seed(3)).to(dev)   # render_buffer_grad ~ N(0,1) seed 3
     r = _native.NativeRenderer(sc["faces"], sc["texcoords"], N, C, W, H, "vertexColor", "shaded", 1, 1, False, dev)
+    r.reserve(B)
+    if B > 1:
+        r.set_option("shared_batch_grads", 1)   # colour / SH gradients summed over the local batch by the backward itself: [1, ...] outputs
     if args.tile:
         r.set_option("tile", args.tile)
     for kv in args.opt:                       # experiments: gvv_set_option knobs, e.g. --opt heavy_mode=0
         k, v = kv.split("=")
         r.set_option(k, int(v))
 
-    # the gradients of the parameters shared across ranks (SH, colours) are written back to back into one flat
-    # buffer, so that the per-step collective is ONE in-place all-reduce without pack / unpack kernels
-    _, (gsh_out, gcol_out) = sharding.shared_grad_buffer([(1, C, 27), (1, N, 3)], dev)
+    # The gradients of the parameters shared across ranks (SH, colours) are summed over the GPUs once per step.
+    #   one-shot (default when symmetric memory is available): the backward writes them into a peer-mapped symmetric buffer and
+    #     a few CTAs inside its last kernel add the W copies over NVLink (peer loads, or NVLS multimem.ld_reduce) -- no NCCL call,
+    #     no extra launch (sharding.SymmetricGradBuffer, csrc/gvv_collective.cuh);
+    #   nccl: they are written back to back into one flat buffer and reduced by ONE in-place NCCL all-reduce after the backward.
+    shared_shapes = [(1, C, 27), (1, N, 3)]
+    symbuf, collective = None, "none"
+    if world > 1 and args.collective == "none":
+        collective = "NONE (diagnostic run: the ranks never exchange anything; not a valid result)"
+    elif world > 1:
+        collective = "nccl"
+        if args.collective != "nccl":
+            try:
+                symbuf = sharding.SymmetricGradBuffer(shared_shapes, dev, mode=args.collective)
+                collective = "one-shot " + symbuf.mode
+            except Exception as e:
+                if args.collective != "auto":
+                    raise
+                sys.stderr.write(f"symmetric memory unavailable ({e!r}); NCCL all-reduce instead\n")
+    _, (gsh_out, gcol_out) = sharding.shared_grad_buffer(shared_shapes, dev)
+    step_no = [0]
 
     def step():
         bary, face, render, vn, _, _ = r.forward(*ins)
+        if symbuf is not None:
+            slot = step_no[0] & 1
+            step_no[0] += 1
+            sg = sharding.SharedGrads(symbuf, slot, ("sh_coeff", "vertex_color"))
+            symbuf.attach(r, slot)
+            gpos = r.backward(G, None, ins[0], ins[1], ins[2], ins[3], ins[4], vn, bary, face, ins[5], ins[6], out=sg.outputs())[0]
+            r.set_allreduce(None)
+            return gpos, symbuf.results(slot)
         gpos, gcol, gtex, gsh = r.backward(G, None, ins[0], ins[1], ins[2], ins[3], ins[4], vn, bary, face, ins[5], ins[6],
                                            out=(None, gcol_out, None, gsh_out))
-        if world > 1:
+        if world > 1 and args.collective != "none":
             sharding.allreduce_shared_grads([gsh, gcol])
-        return gpos
+        return gpos, (gsh, gcol)
 
     def barrier():
         if world > 1:
@@ -147,6 +187,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     host_ms = [0.0]
+    per_rank_ms = []
 
     def timed(fn, k, finalize=None):
         barrier()
@@ -162,6 +203,9 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
+            allms = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(allms, ms)
+            per_rank_ms[:] = [round(float(x) / k, 4) for x in allms]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         barrier()
         return float(ms)
@@ -171,8 +215,33 @@ def run_ours(args, rank, world, local_rank):
     l0 = r.launch_count
     sampler = ClockSampler(local_rank) if rank == 0 else None   # samples through all three timed passes below
     ms = timed(step, args.steps)
+    resident_per_rank_ms = list(per_rank_ms)
     launches = r.launch_count - l0
     value = world * V * args.steps / (ms * 1e-3)
+
+    # ---- untimed N > 1 check: the summed gradients every rank holds equal the sum ONE GPU computes alone over all ranks' seeded
+    # batch elements (rank 0 renders them one after the other) ----
+    multi_check = None
+    if world > 1:
+        _, (red_sh, red_col) = step()
+        red_sh, red_col = red_sh.clone(), red_col.clone()
+        torch.cuda.synchronize()
+        if rank == 0:
+            want_sh = torch.zeros((1, C, 27), dtype=torch.float64, device=dev)
+            want_col = torch.zeros((1, N, 3), dtype=torch.float64, device=dev)
+            for q in range(world):
+                e = make_inputs(q, args.workload)
+                ei = [torch.as_tensor(e[k], device=dev) for k in INPUT_KEYS]
+                o = r.forward(*ei)
+                g = r.backward(G, None, ei[0], ei[1], ei[2], ei[3], ei[4], o[3], o[0], o[1], ei[5], ei[6])
+                want_col += g[1].double().sum(0, keepdim=True)
+                want_sh += g[3].double().sum(0, keepdim=True)
+                del ei, o, g
+            rel = lambda a, b: float((a.double() - b).norm() / b.norm())
+            multi_check = {"sh_coeff_grad_rel_l2": rel(red_sh, want_sh), "vertex_color_grad_rel_l2": rel(red_col, want_col),
+                           "against": f"rank 0 alone over the {world} ranks' batch elements", "tolerance": 1e-5}
+            multi_check["status"] = "pass" if max(multi_check["sh_coeff_grad_rel_l2"], multi_check["vertex_color_grad_rel_l2"]) <= 1e-5 else "FAIL"
+        barrier()
 
     # per-kernel device time (CUDA events on the launching stream) over another K steps
     r.set_option("time_kernels", 1)
@@ -209,7 +278,8 @@ def run_ours(args, rank, world, local_rank):
                 "kernel_ms_per_step": {k: round(v[0] / max(1, args.steps), 4) for k, v in sorted(kt.items())}, "issue": issue}
 
     # ---- e2e: public Python API, host buffers in pinned memory ----
-    host = {k: torch.as_tensor(sc[k]).pin_memory() for k in ("vertex_pos", "vertex_color", "sh_coeff", "extrinsics", "intrinsics")}
+    host = {k: torch.as_tensor(sc[k][:1] if k in ("vertex_color", "sh_coeff") else sc[k]).pin_memory()
+            for k in ("vertex_pos", "vertex_color", "sh_coeff", "extrinsics", "intrinsics")}     # colours and SH: ONE shared set, [1, ...]
     faces_l, tcs_l = sc["faces"].reshape(-1), sc["texcoords"].reshape(-1)
     out_host = {k: torch.empty_like(host[k]).pin_memory() for k in ("vertex_pos", "vertex_color", "sh_coeff")}
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
@@ -231,17 +301,30 @@ def run_ours(args, rank, world, local_rank):
     it = [0]
     GRAD_KEYS = ("vertex_pos", "vertex_color", "sh_coeff")
 
-    def user_step(d):
-        """One fit step through the public API on device inputs d; returns (loss, gradients in GRAD_KEYS order)."""
+    # e2e has its own symmetric buffer (its slots alternate with the e2e step count, independently of the resident-input leg)
+    symbuf_e2e = None
+    if symbuf is not None:
+        symbuf_e2e = sharding.SymmetricGradBuffer(shared_shapes, dev, mode=symbuf.mode)
+
+    def user_step(d, slot):
+        """One fit step through the public API on device inputs d; returns (loss, gradients in GRAD_KEYS order).
+        Colours and SH are parameters shared across the batch: [1, ...] leaves expanded to the op's [B, ...] inputs (autograd
+        sums their gradients over the batch).  With symmetric memory the layer is told to hand those two gradients to the
+        one-shot all-reduce inside its backward (sharedGrads_attr): autograd then receives the sums over all GPUs."""
         leaves = {k: d[k].detach().requires_grad_(True) for k in GRAD_KEYS}
+        shared = None
+        if symbuf_e2e is not None and B == 1:
+            shared = sharding.SharedGrads(symbuf_e2e, slot, ("sh_coeff", "vertex_color"))
         layer = CudaRendererGpu(faces_attr=faces_l, texCoords_attr=tcs_l, numberOfVertices_attr=N, numberOfCameras_attr=C,
                                 renderResolutionU_attr=W, renderResolutionV_attr=H, albedoMode_attr="vertexColor",
-                                shadingMode_attr="shaded", vertexPos_input=leaves["vertex_pos"], vertexColor_input=leaves["vertex_color"],
-                                texture_input=ins[2], shCoeff_input=leaves["sh_coeff"], targetImage_input=ins[4],
-                                extrinsics_input=d["extrinsics"], intrinsics_input=d["intrinsics"], device=dev)
+                                shadingMode_attr="shaded", vertexPos_input=leaves["vertex_pos"], vertexColor_input=leaves["vertex_color"].expand(B, -1, -1),
+                                texture_input=ins[2], shCoeff_input=leaves["sh_coeff"].expand(B, -1, -1), targetImage_input=ins[4],
+                                extrinsics_input=d["extrinsics"], intrinsics_input=d["intrinsics"], device=dev, sharedGrads_attr=shared)
         loss = torch.dot(layer.getRenderBufferTF().reshape(-1), Gflat)   # d loss / d render = G (N(0,1), seed 3), one pass over the image
         grads = torch.autograd.grad(loss, [leaves[k] for k in GRAD_KEYS])
         return loss, grads
+
+    e2e_nccl = world > 1 and args.collective != "none" and not (symbuf_e2e is not None and B == 1)      # otherwise the sum over the GPUs happens inside the captured step
 
     class Slot:
         def __init__(self):
@@ -255,16 +338,17 @@ def run_ours(args, rank, world, local_rank):
         for sl in slots:
             for k, v in host.items():
                 sl.inp[k].copy_(v)
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(comp_s)
-            with torch.cuda.stream(side):          # torch's capture protocol: a few eager runs on a side stream first
-                for _ in range(3):
-                    user_step(sl.inp)
-            comp_s.wait_stream(side)
-            torch.cuda.synchronize()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(comp_s)
+        with torch.cuda.stream(side):              # torch's capture protocol: a few eager runs on a side stream first
+            for n in range(4):
+                user_step(slots[n % 2].inp, n % 2)
+        comp_s.wait_stream(side)
+        torch.cuda.synchronize()
+        for n, sl in enumerate(slots):
             sl.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(sl.graph):
-                sl.loss, sl.grads = user_step(sl.inp)
+                sl.loss, sl.grads = user_step(sl.inp, n)
         torch.cuda.synchronize()
     except Exception as e:                         # capture unavailable: fall back to the eager loop and say so
         sys.stderr.write(f"e2e: CUDA-graph capture failed ({e!r}); eager loop instead\n")
@@ -292,8 +376,8 @@ def run_ours(args, rank, world, local_rank):
             sl.graph.replay()
             loss, grads = sl.loss, sl.grads
         else:
-            loss, grads = user_step(sl.inp)
-        if world > 1:
+            loss, grads = user_step(sl.inp, i % 2)
+        if e2e_nccl:
             sharding.allreduce_shared_grads([grads[2], grads[1]])
         sl.done_ev.record(comp_s)
         sl.uploaded = False
@@ -337,7 +421,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_drain()
     torch.cuda.synchronize()
     if world == 1:
-        chk_loss, chk_grads = user_step({k: v.to(dev) for k, v in host.items()})
+        chk_loss, chk_grads = user_step({k: v.to(dev) for k, v in host.items()}, 0)
         torch.cuda.synchronize()
         for k, g in zip(GRAD_KEYS, chk_grads):
             ref_g, got = g.detach().cpu().double(), out_host[k].double()
@@ -350,17 +434,20 @@ def run_ours(args, rank, world, local_rank):
         e2e["checked"] = "loss and gradients read back by the last timed step equal an eager step on the same inputs (rel-L2 <= 1e-4)"
     # ---- sequential latency: what a fit loop gets, where step i+1's inputs depend on step i's gradients.  ONE slot,
     # everything on one stream, no cross-step overlap: upload -> captured step -> read-back -> host waits, every step ----
-    sl = slots[0]
+    lat_no = [it[0]]                                        # continues the e2e step count: the symmetric slots keep alternating
 
     def latency_step():
+        n = lat_no[0]
+        lat_no[0] += 1
+        sl = slots[n % 2]
         for k, v in host.items():
             sl.inp[k].copy_(v, non_blocking=True)
         if sl.graph is not None:
             sl.graph.replay()
             loss, grads = sl.loss, sl.grads
         else:
-            loss, grads = user_step(sl.inp)
-        if world > 1:
+            loss, grads = user_step(sl.inp, n % 2)
+        if e2e_nccl:
             sharding.allreduce_shared_grads([grads[2], grads[1]])
         for k, g in zip(GRAD_KEYS, grads):
             out_host[k].copy_(g, non_blocking=True)
@@ -381,6 +468,8 @@ def run_ours(args, rank, world, local_rank):
         try:
             from oracle import parity as opar, ref as oref
             if oref.available():
+                if B > 1:
+                    r.set_option("shared_batch_grads", 0)     # the reference's op returns per-batch-element gradients
                 res, _, _, _, _ = opar.check_scene(sc, "vertexColor", "shaded", renderer=r, render_grad=G, dev=dev)
                 parity = {"status": "pass", "against": "oracle/_ref/libgvv_ref.so (the reference's kernels compiled unmodified for sm_100a), same inputs, same GPU",
                           "protocol": "camera matrices, projected vertices, vertex normals, barycentrics, render buffer bit-equal; face buffer equal up to proven "
@@ -417,11 +506,13 @@ def run_ours(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD_NAME,
+                "config": {"workload": wl["name"],
                            "views_per_step_per_gpu": V, "tile": args.tile or 32,
                            "l2": "no explicit flush: a step streams ~300 MB of buffers (192 MB outputs + 100 MB render gradient) through a 126 MB L2",
-                           "collective": "none" if world == 1 else "1 NCCL all-reduce/step of shared SH + colour gradients (%d B)" % ((C * 27 + N * 3) * 4)},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
+                           "collective": "none" if world == 1 else "%s all-reduce of the shared SH + colour gradients, %d B per step%s" % (
+                               collective, (C * 27 + N * 3) * 4, "" if symbuf is None else " (CTAs inside the backward's last kernel, no NCCL call)")},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "multi_gpu_check": multi_check,
+                "ms_per_step_per_rank": resident_per_rank_ms or None}
         print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -433,6 +524,7 @@ def cpu_port_baseline(sc, seconds_budget=20.0, cameras=2):
     cpu.build()
     N, W, H = sc["num_vertices"], sc["width"], sc["height"]
     C = cameras
+    sc = {k: (v[:1] if isinstance(v, np.ndarray) and k in INPUT_KEYS else v) for k, v in sc.items()}     # first batch element
     sl = lambda a, n: np.ascontiguousarray(a.reshape(1, sc["num_cameras"], n)[:, :C].reshape(1, C * n))
     ex, it = sl(sc["extrinsics"], 12), sl(sc["intrinsics"], 9)
     sh = np.ascontiguousarray(sc["sh_coeff"][:, :C])
@@ -451,7 +543,7 @@ def cpu_port_baseline(sc, seconds_budget=20.0, cameras=2):
         if dt > seconds_budget / 2 or reps >= 64:
             break
     return {"value": round(reps * C / dt, 3), "unit": UNIT, "cores": cpu.max_threads(), "kind": "port", "inside_test_hits_per_view": frag_per_view,
-            "sample": f"cameras 0..{C - 1} of the 8 at full size (70k tris, 1024x1024), fwd+bwd, {reps} repetition(s), {dt:.1f} s"}
+            "sample": f"cameras 0..{C - 1} of batch element 0 at full size (70k tris, 1024x1024), fwd+bwd, {reps} repetition(s), {dt:.1f} s"}
 
 
 def run_reference(args, rank, world, local_rank):
@@ -524,6 +616,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS), help="config2 = the bench line; config4 = B=8 x C=16 per GPU (BASELINE.json config 4)")
+    ap.add_argument("--collective", default="auto", choices=["auto", "nccl", "p2p", "nvls", "none"],
+                    help="N > 1: how the shared gradients are summed (auto = one-shot over symmetric memory, NVLS when available, else NCCL)")
     ap.add_argument("--opt", action="append", default=[], help="key=value for gvv_set_option (experiments; applies to the resident-input leg)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -52,7 +52,7 @@ class gvv_allreduce_desc(ctypes.Structure):
     _fields_ = [("peer_buffers", ctypes.c_void_p), ("signal_pads", ctypes.c_void_p), ("multicast_ptr", ctypes.c_uint64),
                 ("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("offset_floats", ctypes.c_int64), ("count_floats", ctypes.c_int64),
                 ("result", ctypes.c_void_p), ("mode", ctypes.c_int32), ("channels", ctypes.c_int32), ("first_channel", ctypes.c_int32),
-                ("after_backward", ctypes.c_int32)]
+                ("epoch_word", ctypes.c_int32), ("after_backward", ctypes.c_int32)]
 
 
 _lib = None

@@ -390,12 +390,13 @@ extern "C" int gvv_set_allreduce(gvv_handle h, const gvv_allreduce_desc* d) {
   if (d->mode != 0 && d->mode != 1) return fail(GVV_EINVAL, "gvv_set_allreduce: mode must be 0 (peer loads) or 1 (NVLS multimem.ld_reduce)");
   if (d->mode == 1 && (!d->multicast_ptr || (d->count_floats & 3))) return fail(GVV_EINVAL, "gvv_set_allreduce: NVLS mode needs a multicast mapping and a count that is a multiple of 4");
   if (d->channels < 1 || d->channels > 64 || d->first_channel < 0) return fail(GVV_EINVAL, "gvv_set_allreduce: channels must be in [1,64]");
+  if (d->epoch_word < (d->first_channel + d->channels) * d->world) return fail(GVV_EINVAL, "gvv_set_allreduce: epoch_word overlaps the signal words");
   ARParams a;
   a.peers = reinterpret_cast<const float* const*>(d->peer_buffers);
   a.pads = reinterpret_cast<uint32_t* const*>(d->signal_pads);
   a.mc = reinterpret_cast<const float*>(d->multicast_ptr);
   a.result = d->result; a.offset = d->offset_floats; a.count = d->count_floats;
-  a.rank = d->rank; a.world = d->world; a.mode = d->mode; a.blocks = d->channels; a.channelBase = d->first_channel;
+  a.rank = d->rank; a.world = d->world; a.mode = d->mode; a.blocks = d->channels; a.channelBase = d->first_channel; a.epochBase = d->epoch_word;
   h->ar = a; h->arAfter = d->after_backward ? 1 : 0;
   return GVV_OK;
 }

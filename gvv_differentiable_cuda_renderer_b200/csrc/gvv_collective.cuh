@@ -24,7 +24,7 @@
 
 namespace gvv {
 
-constexpr int kMaxWorld = 16;
+constexpr int kMaxWorld = 8;    // one NVSwitch domain of this path: the 8 GPUs of a box
 
 struct ARParams {
   const float* const* peers;   // DEVICE array [world]: base of every rank's symmetric buffer (own included)
@@ -34,15 +34,20 @@ struct ARParams {
   long long offset, count;     // range in floats inside every buffer; offset is a multiple of 4
   int rank, world, mode;       // mode 0 = peer loads, 1 = NVLS multimem.ld_reduce
   int blocks, channelBase;     // CTAs taking part (0 = no collective); signal word = (channelBase + block) * world + peer
+  int epochBase;               // word index (own pad) of the per-CTA barrier counters: epochBase + block
 };
 
-__device__ __forceinline__ void ar_put(uint32_t* addr) {     // 0 -> 1, release at system scope
-  unsigned old;
-  do { asm volatile("atom.global.release.sys.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(addr) : "memory"); } while (old != 0u);
+// Barrier signals are monotonic counters: arriving at barrier number e, a CTA adds 1 to its word in every peer's pad
+// (fire-and-forget red, release at system scope: no NVLink round trip to wait for) and spins on its own pad until the
+// word of every peer has reached e.  Nothing is ever reset, so a rank that runs ahead cannot be confused with a
+// previous barrier; the counter e lives in the CTA's own pad and only that CTA touches it.
+__device__ __forceinline__ void ar_signal(uint32_t* addr) {
+  asm volatile("red.release.sys.global.add.u32 [%0], 1;" :: "l"(addr) : "memory");
 }
-__device__ __forceinline__ void ar_wait(uint32_t* addr) {    // 1 -> 0, acquire at system scope
-  unsigned old;
-  do { asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], 1, 0;" : "=r"(old) : "l"(addr) : "memory"); } while (old != 1u);
+__device__ __forceinline__ unsigned ar_poll(const uint32_t* addr) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ float4 ar_ld_sys(const float* p) {
   float4 v;
@@ -64,30 +69,46 @@ __device__ __forceinline__ float4 ar_ld_reduce(const float* mc) {   // the switc
 // One CTA's share of the all-reduce; every thread of the CTA calls it (it contains a block barrier).
 __device__ __forceinline__ void allreduce_block(const ARParams& a, int block) {
   const int tid = threadIdx.x, nth = blockDim.x;
+  uint32_t* epochWord = a.pads[a.rank] + a.epochBase + block;
+  unsigned epoch = 0;
   if (tid < a.world) {
     const size_t word = (size_t)(a.channelBase + block) * a.world;
+    epoch = *reinterpret_cast<volatile uint32_t*>(epochWord) + 1u;      // this CTA's barrier number (written back below)
     __threadfence_system();
-    ar_put(a.pads[tid] + word + a.rank);        // tell peer `tid` that this rank's gradients are complete
-    ar_wait(a.pads[a.rank] + word + tid);       // wait until peer `tid` says the same, and reset the word
+    ar_signal(a.pads[tid] + word + a.rank);                              // tell peer `tid`: this rank's gradients are complete
+    const uint32_t* mine = a.pads[a.rank] + word + tid;
+    while ((int)(ar_poll(mine) - epoch) < 0) { }                         // until peer `tid` has said the same for this barrier
   }
   __syncthreads();
+  if (tid == 0) *reinterpret_cast<volatile uint32_t*>(epochWord) = epoch;
+  // Remote loads cost a full NVLink round trip (microseconds) each, so the exchange is sized to be ONE round trip deep:
+  // every thread issues all the loads of two float4 columns (2 x W peer loads, or 2 multimem loads) before it adds anything,
+  // and the caller picks enough CTAs that the range is covered in about one such pass (sharding.SymmetricGradBuffer).
   const long long n4 = a.count >> 2;
-  for (long long i = (long long)block * nth + tid; i < n4; i += (long long)a.blocks * nth) {
-    const long long off = a.offset + 4 * i;
-    float4 s;
+  const long long stride = (long long)a.blocks * nth;
+  for (long long i0 = (long long)block * nth + tid; i0 < n4; i0 += 2 * stride) {
+    const long long i1 = i0 + stride;
+    const bool two = i1 < n4;
+    const long long off0 = a.offset + 4 * i0, off1 = a.offset + 4 * (two ? i1 : i0);
+    float4 s0, s1;
     if (a.mode == 1) {
-      s = ar_ld_reduce(a.mc + off);
+      s0 = ar_ld_reduce(a.mc + off0);
+      s1 = ar_ld_reduce(a.mc + off1);
     } else {
-      float4 v[kMaxWorld];
+      float4 v0[kMaxWorld], v1[kMaxWorld];
 #pragma unroll
       for (int p = 0; p < kMaxWorld; ++p)
-        if (p < a.world) v[p] = ar_ld_sys(a.peers[p] + off);      // all W loads in flight, then a fixed-order sum
-      s = v[0];
+        if (p < a.world) { v0[p] = ar_ld_sys(a.peers[p] + off0); v1[p] = ar_ld_sys(a.peers[p] + off1); }
+      s0 = v0[0]; s1 = v1[0];
 #pragma unroll
-      for (int p = 1; p < kMaxWorld; ++p)
-        if (p < a.world) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
+      for (int p = 1; p < kMaxWorld; ++p)                            // fixed rank order: the same bits on every rank
+        if (p < a.world) {
+          s0.x += v0[p].x; s0.y += v0[p].y; s0.z += v0[p].z; s0.w += v0[p].w;
+          s1.x += v1[p].x; s1.y += v1[p].y; s1.z += v1[p].z; s1.w += v1[p].w;
+        }
     }
-    *reinterpret_cast<float4*>(a.result + 4 * i) = s;
+    *reinterpret_cast<float4*>(a.result + 4 * i0) = s0;
+    if (two) *reinterpret_cast<float4*>(a.result + 4 * i1) = s1;
   }
   if (block == 0 && tid < (int)(a.count & 3)) {                    // tail of a count that is not a multiple of 4
     const long long i = (n4 << 2) + tid;

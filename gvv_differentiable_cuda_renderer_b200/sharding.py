@@ -239,7 +239,7 @@ class SymmetricGradBuffer:
 
     FIRST_CHANNEL = 16
 
-    def __init__(self, shapes, device, group=None, mode="auto", channels=16, after_backward=False):
+    def __init__(self, shapes, device, group=None, mode="auto", channels=None, after_backward=False):
         import torch.distributed._symmetric_memory as symm_mem
         from . import _native
         self._native = _native
@@ -262,7 +262,10 @@ class SymmetricGradBuffer:
             raise RuntimeError("SymmetricGradBuffer: NVLS requested but the allocation has no multicast mapping")
         self.mode = mode
         pad_words = int(symm_mem.get_signal_pad_size()) // 4
-        self.channels = max(1, min(int(channels), pad_words // self.world - self.FIRST_CHANNEL, 64))
+        if channels is None:        # one pass of 2 float4 per thread over the range: remote loads are latency-bound (~1 NVLink round trip)
+            channels = max(4, -(-self.slot // 4 // 512))
+        self.epoch_word = pad_words - 64                    # the last 64 words of the pad: one barrier counter per CTA
+        self.channels = max(1, min(int(channels), self.epoch_word // self.world - self.FIRST_CHANNEL, 64))
         self.after_backward = bool(after_backward)
         self.result = torch.empty(2 * self.slot, dtype=torch.float32, device=self.device)   # one per slot: step i's sums stay readable during step i+1
         self._descs = []
@@ -270,7 +273,7 @@ class SymmetricGradBuffer:
             d = _native.gvv_allreduce_desc(int(self.hdl.buffer_ptrs_dev), int(self.hdl.signal_pad_ptrs_dev), mc if mode == "nvls" else 0,
                                            self.rank, self.world, s * self.slot, self.slot if mode == "nvls" else self.count,
                                            self.result.data_ptr() + 4 * s * self.slot, 1 if mode == "nvls" else 0, self.channels, self.FIRST_CHANNEL,
-                                           int(self.after_backward))
+                                           self.epoch_word, int(self.after_backward))
             self._descs.append(d)
         torch.cuda.synchronize(self.device)
         dist.barrier(group=group)          # every rank's buffer is zeroed and mapped before anyone's first step

@@ -135,8 +135,9 @@ const char* gvv_last_error(void);
  * of every rank's SYMMETRIC buffer (each rank passes gradient output pointers inside its own buffer to gvv_backward)
  * into `result` on every rank:  result[i] = sum over ranks r of peer_buffers[r][offset_floats + i], rank order 0..W-1.
  *   peer_buffers   DEVICE array [world] of the base addresses, as mapped in THIS process, of every rank's buffer
- *   signal_pads    DEVICE array [world] of uint32 signal pads (zero-initialised; words (first_channel + c) * world + r,
- *                  c < channels, are used and left zero)
+ *   signal_pads    DEVICE array [world] of uint32 signal pads, zero-initialised and from then on touched only by this
+ *                  library: words (first_channel + c) * world + r, c < channels, are monotonic barrier counters, words
+ *                  epoch_word + c hold each CTA's barrier number (epoch_word >= (first_channel + channels) * world)
  *   multicast_ptr  NVLS multicast mapping of the buffer (0 if none); mode 1 reads the sum from the switch
  *   after_backward 0: the range holds only gradients that are final after the per-pixel kernel (SH, colours, texture):
  *                  the exchange runs as `channels` CTAs INSIDE the backward's last kernel, overlapped with its math;
@@ -153,6 +154,7 @@ typedef struct gvv_allreduce_desc {
   int32_t     mode;            /* 0 = peer loads over NVLink (ld.global.sys), 1 = NVLS multimem.ld_reduce */
   int32_t     channels;        /* CTAs taking part, 1..64 */
   int32_t     first_channel;
+  int32_t     epoch_word;
   int32_t     after_backward;
 } gvv_allreduce_desc;
 int gvv_set_allreduce(gvv_handle h, const gvv_allreduce_desc* desc);
