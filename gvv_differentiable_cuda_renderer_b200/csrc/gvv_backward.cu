@@ -94,6 +94,24 @@ __device__ __forceinline__ void bary_vjp_fast(V3 o, V3 d, V3 v0, V3 v1, V3 v2, f
 
 __device__ __forceinline__ V3 ld4(const float4* __restrict__ p, size_t i) { const float4 v = __ldg(p + i); return v3(v.x, v.y, v.z); }
 
+// mbarrier + bulk async copy (TMA) helpers for the staged input tile of pixel_grad_kernel
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smemDst, const void* gsrc, int bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"((unsigned)__cvta_generic_to_shared(smemDst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
 // grid (W/32, H/32, V), 256 threads: the CTA owns a 32x32 pixel tile, warp w the 32-pixel scanline segments
 // y = 32*by + 8*s + w of its four 8-row slabs s.  All four face ids of a thread are loaded up front, so an empty
 // tile (about 40 % of them at 50 % coverage) costs ONE memory round trip and one barrier; the warps then run
@@ -103,34 +121,71 @@ constexpr int kSlabs = 4;
 // SHADED is a template parameter: the shaded instance is the full chain; the shadeless one drops, at compile time,
 // everything its gradients do not depend on (SH basis and light, the albedo VALUE and its texel / colour gathers,
 // the shading-normal position term and its buffers), which the register allocator could not do behind a runtime flag.
-template <bool SHADED, int ALBEDO>
-__global__ void __launch_bounds__(256, 4)
+template <bool SHADED, int ALBEDO, bool STAGED>
+__global__ void __launch_bounds__(256, 3)
 pixel_grad_kernel(const PixelParams p) {
   chain_wait(); chain_trigger();
   extern __shared__ __align__(16) float buf_dyn[];   // per warp: (kVals + kShRows + kIdRows) rows, value-major, kRow floats per value (32 pixels + pad)
   __shared__ float shPart[8][kVals];
-  __shared__ CamRec cam;
-  __shared__ float shc[27];
+  __shared__ CamRec cam;        // only staged for the model-to-data term (K, E)
+  // The per-view constants are laid out for 128-bit broadcast reads: the kernel was bound by the L1 data pipe
+  // (l1tex__data_pipe_lsu_wavefronts 79 % of peak, profiles/r02_ncu_summaries.md), where a scalar LDS costs a
+  // wavefront like a 128-bit one: 9 instead of 51 reads per pixel for the SH coefficients, 4 instead of 15 for the ray.
+  __shared__ float4 shc4[9];    // channel ch: coefficients 0..8 in shc4[3 ch .. 3 ch + 2] (three pad words)
+  __shared__ float4 camv[4];    // rows 0..2 of (K E)^-1, ray origin
 
   const int view = blockIdx.z, b = (int)(((float)view + 0.5f) * p.invC);   // = view / C without the integer division (exact below 2^22 views)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int x = blockIdx.x * 32 + lane;
   const size_t viewBase = (size_t)view * p.W * p.H;
+  // STAGED (off: measured slower, 0.214 -> 0.245 ms): the tile's inputs (face 4 KB, then -- only when something is visible -- bary 8 KB + render_grad 12 KB)
+  // arrive by bulk async copies (TMA), one 128 / 256 / 384-byte row per copy, completion on two mbarriers: the
+  // first hop of the face -> triangle -> vertices chain is off every warp's critical path and the per-pixel
+  // loads (two of them at a 12-byte stride) become shared-memory reads.  Border tiles and unaligned images
+  // keep the direct loads.
+  __shared__ __align__(8) unsigned long long mbar[2];
+  int* sFace = reinterpret_cast<int*>(buf_dyn + 8 * kWarpBufFloats);
+  float2* sBary = reinterpret_cast<float2*>(sFace + 1024);
+  float* sRg = reinterpret_cast<float*>(sBary + 1024);
+  const bool staged = STAGED && ((p.W & 3) == 0) && (int)blockIdx.x * 32 + 32 <= p.W && (int)blockIdx.y * 32 + 32 <= p.H &&
+                      ((reinterpret_cast<uintptr_t>(p.face) | reinterpret_cast<uintptr_t>(p.bary) | reinterpret_cast<uintptr_t>(p.render_grad)) & 15) == 0;
+  const size_t tileRow0 = viewBase + (size_t)(blockIdx.y * 32) * p.W + blockIdx.x * 32;   // first pixel of row 0 of the tile
   bool any = false;
+  if (staged) {
+    if (tid == 0) { mbar_init(&mbar[0], 32); mbar_init(&mbar[1], 32); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    if (tid < 32) { mbar_expect_tx(&mbar[0], 128); bulk_load(sFace + tid * 32, p.face + tileRow0 + (size_t)tid * p.W, 128, &mbar[0]); }
+  } else {
 #pragma unroll
-  for (int s = 0; s < kSlabs; ++s) {
-    const int ys = blockIdx.y * 32 + s * 8 + warp;
-    const int f = (x < p.W && ys < p.H) ? __ldg(p.face + viewBase + (size_t)ys * p.W + x) : -1;
-    any = any || f >= 0;
+    for (int s = 0; s < kSlabs; ++s) {
+      const int ys = blockIdx.y * 32 + s * 8 + warp;
+      const int f = (x < p.W && ys < p.H) ? __ldg(p.face + viewBase + (size_t)ys * p.W + x) : -1;
+      any = any || f >= 0;
+    }
   }
   constexpr bool shaded = SHADED;
   constexpr int albedo = ALBEDO;       // vertexColor | textured | foregroundMask (the other modes have no gradient)
 
   // camera + SH staging overlaps the latency of the face loads; ONE barrier publishes both and
   // tells whether anything is visible in this 32x32 tile
-  if (tid < 64) reinterpret_cast<float*>(&cam)[tid] = __ldg(reinterpret_cast<const float*>(p.cams + view) + tid);
-  if (tid >= 64 && tid < 64 + 27) shc[tid - 64] = __ldg(p.sh_coeff + (size_t)view * 27 + (tid - 64));
+  if (tid < 64) { if (p.target_grad) reinterpret_cast<float*>(&cam)[tid] = __ldg(reinterpret_cast<const float*>(p.cams + view) + tid); }
+  else if (tid < 64 + 36) { const int i = tid - 64, ch = i / 12, k = i - 12 * ch; reinterpret_cast<float*>(shc4)[i] = k < 9 ? __ldg(p.sh_coeff + (size_t)view * 27 + ch * 9 + k) : 0.f; }
+  else if (tid >= 128 && tid < 128 + 16) {
+    const int i = tid - 128;
+    const CamRec* cr = p.cams + view;
+    reinterpret_cast<float*>(camv)[i] = i < 12 ? __ldg(cr->Pinv + i) : (i < 15 ? __ldg(cr->ro + (i - 12)) : 0.f);
+  }
+  if (staged) {
+    mbar_wait(&mbar[0], 0);
+#pragma unroll
+    for (int s = 0; s < kSlabs; ++s) any = any || sFace[(s * 8 + warp) * 32 + lane] >= 0;
+  }
   if (__syncthreads_or(any) == 0) return;
+  if (staged && tid < 32) {
+    mbar_expect_tx(&mbar[1], 640);
+    bulk_load(sBary + tid * 32, p.bary + 2 * (tileRow0 + (size_t)tid * p.W), 256, &mbar[1]);
+    bulk_load(sRg + tid * 96, p.render_grad + 3 * (tileRow0 + (size_t)tid * p.W), 384, &mbar[1]);
+  }
 
   float* mybuf = buf_dyn + warp * kWarpBufFloats;
   float* mine = mybuf + lane;   // value j of this lane's pixel lives at mine[j * kRow]
@@ -140,7 +195,8 @@ pixel_grad_kernel(const PixelParams p) {
   for (int slab = 0; slab < kSlabs; ++slab) {
   const int y = blockIdx.y * 32 + slab * 8 + warp;
   const size_t pix = viewBase + (size_t)y * p.W + x;
-  const int face = (x < p.W && y < p.H) ? __ldg(p.face + pix) : -1;      // second read of the line: L1/L2 hit
+  const int spix = (slab * 8 + warp) * 32 + lane;                          // pixel index inside the staged tile
+  const int face = staged ? sFace[spix] : ((x < p.W && y < p.H) ? __ldg(p.face + pix) : -1);      // (not staged: second read of the line: L1/L2 hit)
   const bool covered = face >= 0;
   const unsigned cv = __ballot_sync(FULL_MASK, covered);
   if (cv == 0) continue;
@@ -152,11 +208,15 @@ pixel_grad_kernel(const PixelParams p) {
   {
     if (covered) {
       // ---- per-pixel setup (CUDABasedRasterizationGrad.cu:205-240) ----
-      const F3 rdx = ray_dir_exact(cam.Pinv, cam.ro, (float)x + 0.5f, (float)y + 0.5f);
-      const V3 d = v3(rdx.x, rdx.y, rdx.z), o = v3(cam.ro[0], cam.ro[1], cam.ro[2]);
-      const float2 ab = __ldg(reinterpret_cast<const float2*>(p.bary) + pix);
-      const float bc[3] = {ab.x, ab.y, 1.f - ab.x - ab.y};
+      const float4 r0 = camv[0], r1 = camv[1], r2 = camv[2], ro4 = camv[3];
+      const float Pv[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+      const float rov[3] = {ro4.x, ro4.y, ro4.z};
+      const F3 rdx = ray_dir_exact(Pv, rov, (float)x + 0.5f, (float)y + 0.5f);
+      const V3 d = v3(rdx.x, rdx.y, rdx.z), o = v3(ro4.x, ro4.y, ro4.z);
       const int4 fc = __ldg(p.faces4 + face);
+      if (staged) mbar_wait(&mbar[1], 0);      // bary + render_grad of the tile have landed (immediate after the first time)
+      const float2 ab = staged ? sBary[spix] : __ldg(reinterpret_cast<const float2*>(p.bary) + pix);
+      const float bc[3] = {ab.x, ab.y, 1.f - ab.x - ab.y};
       mine[(kVals + kShRows + 0) * kRow] = __int_as_float(fc.x);   // vertex ids for the run-end atomics of the scatter stage
       mine[(kVals + kShRows + 1) * kRow] = __int_as_float(fc.y);
       mine[(kVals + kShRows + 2) * kRow] = __int_as_float(fc.z);
@@ -178,14 +238,22 @@ pixel_grad_kernel(const PixelParams p) {
       Y[0] = 1.f; Y[1] = n.y; Y[2] = n.z; Y[3] = n.x; Y[4] = n.x * n.y; Y[5] = n.z * n.y;
       Y[6] = 3.f * n.z * n.z - 1.f; Y[7] = n.x * n.z; Y[8] = n.x * n.x - n.y * n.y;
       float light[3];
+      V3 jl[3];      // JLiNo row of every channel (RendererUtil.h:371-391), from the same three 128-bit reads as the light
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
+        const float4 a4 = shc4[3 * ch], b4 = shc4[3 * ch + 1], c4 = shc4[3 * ch + 2];
+        const float sc[9] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w, c4.x};
         float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) s += shc[ch * 9 + k] * Y[k];
+        for (int k = 0; k < 9; ++k) s += sc[k] * Y[k];
         light[ch] = s;
+        if (shaded)
+          jl[ch] = v3(sc[3] + sc[4] * n.y + sc[7] * n.z + sc[8] * 2.f * n.x,
+                      sc[1] + sc[4] * n.x + sc[5] * n.z + sc[8] * -2.f * n.y,
+                      sc[2] + sc[5] * n.y + sc[6] * 6.f * n.z + sc[7] * n.x);
       }
-      const float3 g = make_float3(__ldg(p.render_grad + 3 * pix), __ldg(p.render_grad + 3 * pix + 1), __ldg(p.render_grad + 3 * pix + 2));
+      const float3 g = staged ? make_float3(sRg[3 * spix], sRg[3 * spix + 1], sRg[3 * spix + 2])
+                              : make_float3(__ldg(p.render_grad + 3 * pix), __ldg(p.render_grad + 3 * pix + 1), __ldg(p.render_grad + 3 * pix + 2));
       const float gl[3] = {shaded ? g.x * light[0] : g.x, shaded ? g.y * light[1] : g.y, shaded ? g.z * light[2] : g.z};
 
       // ---- albedo (:242-319) and its gradients (:327-395) ----
@@ -251,12 +319,7 @@ pixel_grad_kernel(const PixelParams p) {
         // ---- position gradient through the shading normal (:458-525) ----
         V3 u3 = v3(0.f, 0.f, 0.f);   // (g*albedo) * JLiNo  (RendererUtil.h:371-391)
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          const float* s = shc + ch * 9;
-          u3.x += gA[ch] * (s[3] + s[4] * n.y + s[7] * n.z + s[8] * 2.f * n.x);
-          u3.y += gA[ch] * (s[1] + s[4] * n.x + s[5] * n.z + s[8] * -2.f * n.y);
-          u3.z += gA[ch] * (s[2] + s[5] * n.y + s[6] * 6.f * n.z + s[7] * n.x);
-        }
+        for (int ch = 0; ch < 3; ++ch) u3 = u3 + gA[ch] * jl[ch];
         // * JNoNu (:398-415): (len^2 I - nUn nUn^T) / len^3 = (u - (u.n^)n^) / len, UNflipped normal n^ = nUn/len
         const V3 nh = ilen * nUn;
         const float un = dot(u3, nh);
@@ -354,7 +417,7 @@ pixel_grad_kernel(const PixelParams p) {
         if ((endm >> l) & 1u) {
           if (active && acc != 0.f) {
             const int vid = __float_as_int(idrow[l]);        // vertex vi of the triangle pixel l sees (one shared-memory read)
-            atomicAdd(base + (size_t)vid * vstride, acc);
+            atomicAdd(base + (unsigned)(vid * 3 + (arr == 2 ? vid : 0)), acc);   // 32-bit index arithmetic (N * 4 < 2^32): the 64-bit form cost nine instructions per flush
           }
           acc = 0.f;
         }
@@ -514,14 +577,17 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   tm->begin(K_PIXEL_GRAD, st);
   constexpr int kPixelSmem = 8 * kWarpBufFloats * (int)sizeof(float);
   const dim3 pgGrid((a.W + 31) / 32, (a.H + 31) / 32, V);
-#define GVV_PG(S, A) do { static unsigned long long attr = 0; \
-    if (first_use_on_device(&attr)) cudaFuncSetAttribute(pixel_grad_kernel<S, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPixelSmem); \
-    launch_chained(a.chain, pixel_grad_kernel<S, A>, pgGrid, dim3(256), kPixelSmem, st, p); } while (0)
+#define GVV_PG2(S, A, ST) do { static unsigned long long attr = 0; \
+    constexpr int smem = kPixelSmem + ((ST) ? 24576 : 0); \
+    if (first_use_on_device(&attr)) cudaFuncSetAttribute(pixel_grad_kernel<S, A, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+    launch_chained(a.chain, pixel_grad_kernel<S, A, ST>, pgGrid, dim3(256), smem, st, p); } while (0)
+#define GVV_PG(S, A) do { if (a.exp & 16) GVV_PG2(S, A, true); else GVV_PG2(S, A, false); } while (0)
   const bool sh = a.shading == GVV_SHADING_SHADED;
   if (a.albedo == GVV_ALBEDO_VERTEX_COLOR) { if (sh) GVV_PG(true, GVV_ALBEDO_VERTEX_COLOR); else GVV_PG(false, GVV_ALBEDO_VERTEX_COLOR); }
   else if (a.albedo == GVV_ALBEDO_TEXTURED) { if (sh) GVV_PG(true, GVV_ALBEDO_TEXTURED); else GVV_PG(false, GVV_ALBEDO_TEXTURED); }
   else { if (sh) GVV_PG(true, GVV_ALBEDO_FOREGROUND_MASK); else GVV_PG(false, GVV_ALBEDO_FOREGROUND_MASK); }   // foregroundMask (and any mode without an albedo gradient)
 #undef GVV_PG
+#undef GVV_PG2
   tm->end(st);
   ++launches;
   const bool fusedAR = a.ar.blocks > 0 && !a.arAfter;

@@ -523,7 +523,7 @@ struct RasterParams {
   const float* texture; const float* texcoords; const float* sh_coeff;
   float* bary; int32_t* face; float* render;
   unsigned long long* ctaTrace;
-  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, hizMin, spanZ, role, pdl, grid2d, texBilinear, resolvePrefetch;
+  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, hizMin, spanZ, role, pdl, grid2d, texBilinear, resolvePrefetch, exp;
   float cullMargin;
 };
 
@@ -582,8 +582,8 @@ constexpr int kWarpSmemBytes = kBatch * (int)sizeof(TriRec) + kBatch * (int)size
 template <int TS, bool RC, int NTH>
 constexpr int raster_smem_bytes() { return TS * TS * (16 + (RC ? 12 : 0)) + (NTH / 32) * kWarpSmemBytes; }
 
-template <int TS, bool RC, int NTH>
-__global__ void __launch_bounds__(NTH, (RC ? 3 : 4) * (256 / NTH))
+template <int TS, bool RC, int NTH, int OCC = (RC ? 3 : 4)>
+__global__ void __launch_bounds__(NTH, OCC * (256 / NTH))
 raster_kernel(const RasterParams p) {
   constexpr int NPIX = TS * TS;
   constexpr int ZRAY = NPIX * (16 + (RC ? 12 : 0));
@@ -951,6 +951,16 @@ raster_kernel(const RasterParams p) {
       }
     }
   }
+  // Output tile through shared memory + bulk async copies (TMA, cp.async.bulk): the 24 B/px of a tile that lies
+  // inside a 16-byte aligned image are staged in the (by now dead) per-warp batch buffers and leave as 3 x TS
+  // row copies of 128 / 256 / 384 contiguous bytes instead of five scalar stores per pixel, three of them at a
+  // 12-byte stride.  Border tiles, odd widths and strips keep the direct stores.
+  constexpr bool kStageFits = NPIX * 24 <= (NTH / 32) * kWarpSmemBytes;
+  const bool bulkOut = kStageFits && (p.exp & 4) && stripLog == 0 && ((p.W & 3) == 0) && tileX0 + TS <= p.W && tileY0 + TS <= p.H &&
+                       ((reinterpret_cast<uintptr_t>(p.face) | reinterpret_cast<uintptr_t>(p.bary) | reinterpret_cast<uintptr_t>(p.render)) & 15) == 0;
+  int* sFace = reinterpret_cast<int*>(smemRaw + ZRAY);
+  float2* sBary = reinterpret_cast<float2*>(smemRaw + ZRAY + NPIX * 4);
+  float* sRender = reinterpret_cast<float*>(smemRaw + ZRAY + NPIX * 12);
   for (int q = qLo + tid; q < qHi; q += NTH) {
     const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
     if (x >= p.W || y >= p.H) continue;
@@ -1018,9 +1028,30 @@ raster_kernel(const RasterParams p) {
         cb = __fmul_rn(cb, sh_eval(shc + 18, nr));
       }
     }
-    p.face[pix] = faceId;
-    reinterpret_cast<float2*>(p.bary)[pix] = make_float2(a, bq);
-    p.render[3 * pix + 0] = cr; p.render[3 * pix + 1] = cg; p.render[3 * pix + 2] = cb;
+    if (bulkOut) {
+      sFace[q] = faceId;
+      sBary[q] = make_float2(a, bq);
+      sRender[3 * q + 0] = cr; sRender[3 * q + 1] = cg; sRender[3 * q + 2] = cb;
+    } else {
+      p.face[pix] = faceId;
+      reinterpret_cast<float2*>(p.bary)[pix] = make_float2(a, bq);
+      p.render[3 * pix + 0] = cr; p.render[3 * pix + 1] = cg; p.render[3 * pix + 2] = cb;
+    }
+  }
+  if (bulkOut) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the generic-proxy writes above become visible to the copy engine
+    __syncthreads();
+    if (tid < TS) {                                                // one row of the tile per thread: three bulk copies
+      const size_t rowPix = pixBase + (size_t)(tileY0 + tid) * p.W + tileX0;
+      const unsigned sF = (unsigned)__cvta_generic_to_shared(sFace + tid * TS);
+      const unsigned sB = (unsigned)__cvta_generic_to_shared(sBary + tid * TS);
+      const unsigned sR = (unsigned)__cvta_generic_to_shared(sRender + tid * TS * 3);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(p.face + rowPix), "r"(sF), "n"(TS * 4) : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(p.bary + 2 * rowPix), "r"(sB), "n"(TS * 8) : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(p.render + 3 * rowPix), "r"(sR), "n"(TS * 12) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must stay allocated until it has been read
+    }
   }
   // self-cleaning scratch: the last strip of the tile to finish resets the tile's counters (every strip
   // read them before it got here)
@@ -1142,7 +1173,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   p.texture = a.texture; p.texcoords = a.texcoords; p.sh_coeff = a.sh_coeff;
   p.bary = a.bary; p.face = a.face; p.render = a.render; p.ctaTrace = a.s.ctaTrace;
   p.C = a.C; p.N = a.N; p.F = a.F; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
-  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv; p.interleave = a.interleave; p.hiz = a.hiz; p.hizMin = a.hizMin; p.spanZ = a.spanZ; p.texBilinear = a.texBilinear; p.resolvePrefetch = a.resolvePrefetch;
+  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv; p.interleave = a.interleave; p.hiz = a.hiz; p.hizMin = a.hizMin; p.spanZ = a.spanZ; p.texBilinear = a.texBilinear; p.resolvePrefetch = a.resolvePrefetch; p.exp = a.exp;
   p.grid2d = nItems <= 65535 ? 1 : 0;
   const dim3 gridT = p.grid2d ? dim3((unsigned)V, (unsigned)nItems) : dim3((unsigned)nItems * (unsigned)V);
   tm->begin(K_RASTER, st);
@@ -1151,6 +1182,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
 #define GVV_RASTER_ATTR(TS, RC, NTH) cudaFuncSetAttribute(raster_kernel<TS, RC, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<TS, RC, NTH>())
     GVV_RASTER_ATTR(16, true, 256); GVV_RASTER_ATTR(32, true, 256); GVV_RASTER_ATTR(16, false, 256); GVV_RASTER_ATTR(32, false, 256);
     GVV_RASTER_ATTR(16, false, 128); GVV_RASTER_ATTR(32, false, 128); GVV_RASTER_ATTR(32, false, 1024);
+    cudaFuncSetAttribute(raster_kernel<32, false, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<32, false, 256>());
 #undef GVV_RASTER_ATTR
   }
   // The heavy launch goes FIRST, so that its one-SM CTAs are placed while the SMs are empty (behind the small CTAs
@@ -1183,6 +1215,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
     } else {
       if (a.rayCache) GVV_RASTER_LAUNCH(32, true, 256);
       else if (a.ctaThreads == 128) GVV_RASTER_LAUNCH(32, false, 128);
+      else if (a.exp & 32) { cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = raster_smem_bytes<32, false, 256>(); cudaLaunchKernelEx(&cfg, raster_kernel<32, false, 256, 3>, p); }
       else GVV_RASTER_LAUNCH(32, false, 256);
     }
 #undef GVV_RASTER_LAUNCH

@@ -85,6 +85,7 @@ struct gvv_renderer {
   int interleave = 1;         // raster: batch j takes bin entries j, j+nBatches, ... instead of a contiguous chunk
   int ctaThreads = 256;       // raster: threads per tile CTA (256 | 128)
   int batchDiv = 8;           // raster: a bin of n triangles is cut into batches of ceil(n / batchDiv) (<= 32) triangles
+  int exp = 0;                // development: bit mask of experimental code paths under A/B measurement (tools/gpu_ab.py); 0 in production
   int rayCache = 0;           // raster: 1 = per-pixel ray cache in shared memory (3 CTAs/SM), 0 = recompute (4 CTAs/SM, measured faster)
   float cullMargin = 0.0625f; // px (fixed part of the margin); < 0 disables the conservative screen-space pre-test
   bool hasTexcoords = false;
@@ -105,7 +106,7 @@ namespace gvv {
 
 struct FwdArgs {
   int B, C, N, F, W, H, texH, texW, albedo, shading;
-  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, hizMin, spanZ, splitUnit, heavyThr, heavyMode, heavySlots, ctaSlots, spreadEmpty, texBilinear, resolvePrefetch, chain;
+  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, hizMin, spanZ, splitUnit, heavyThr, heavyMode, heavySlots, ctaSlots, spreadEmpty, texBilinear, resolvePrefetch, chain, exp;
   float cullMargin;
   const float *vertex_pos, *vertex_color, *texture, *sh_coeff, *extrinsics, *intrinsics;
   const float* texcoords;
@@ -116,7 +117,7 @@ struct FwdArgs {
 };
 
 struct BwdArgs {
-  int B, C, N, F, W, H, texH, texW, albedo, shading, imgFilter, texBilinear, chain, sharedBatch;
+  int B, C, N, F, W, H, texH, texW, albedo, shading, imgFilter, texBilinear, chain, sharedBatch, exp;
   const float *render_grad, *target_grad, *vertex_pos, *vertex_color, *texture, *sh_coeff, *target_image,
       *vertex_normal, *bary, *extrinsics, *intrinsics, *texcoords, *target_du, *target_dv;
   const int32_t* face;
