@@ -42,7 +42,7 @@ static cudaError_t dmalloc(T** p, size_t count) {
 static void free_scratch(Scratch& s) {
   cudaFree(s.cams); cudaFree(s.proj); cudaFree(s.vscaled); cudaFree(s.fnorm4); cudaFree(s.vnorm4); cudaFree(s.vcol4);
   cudaFree(s.tileCount); cudaFree(s.tileCursor); cudaFree(s.tileCursorFar); cudaFree(s.tileMinK); cudaFree(s.tileMaxK); cudaFree(s.tileThr); cudaFree(s.tileOffset); cudaFree(s.tileOrder); cudaFree(s.tileDone); cudaFree(s.bigCount);
-  cudaFree(s.bigList); cudaFree(s.bins); cudaFree(s.gnorm); cudaFree(s.bpos4); cudaFree(s.bcol4); cudaFree(s.bnor4); cudaFree(s.ctaTrace);
+  cudaFree(s.bigList); cudaFree(s.bins); cudaFree(s.gnorm); cudaFree(s.bpos4); cudaFree(s.bcol4); cudaFree(s.bnor4); cudaFree(s.tileCounter); cudaFree(s.ctaTrace);
   s = Scratch();
 }
 
@@ -99,6 +99,7 @@ static int ensure_scratch(gvv_renderer* h, int B, cudaStream_t st) {
   acc(dmalloc(&s.bpos4, (size_t)B * N));
   acc(dmalloc(&s.bcol4, (size_t)B * N));
   acc(dmalloc(&s.bnor4, (size_t)V * N));
+  acc(dmalloc(&s.tileCounter, (size_t)4));
   if (h->ctaTrace) acc(dmalloc(&s.ctaTrace, (size_t)V * (nT + nT / 2) * 4));
   if (e != cudaSuccess) {
     free_scratch(s);
@@ -253,6 +254,7 @@ extern "C" int gvv_set_option(gvv_handle h, const char* key, int32_t value) {
   if (!strcmp(key, "cta_trace")) { if (h->captured) return fail(GVV_EINVAL, "cta_trace cannot change after the handle was used under stream capture"); cudaSetDevice(h->device); cudaDeviceSynchronize(); free_scratch(h->s); h->ctaTrace = value ? 1 : 0; return GVV_OK; }   // scratch is re-allocated by the next call
   if (!strcmp(key, "shared_batch_grads")) { h->sharedBatchGrads = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "texture_bilinear")) { h->texBilinear = value ? 1 : 0; return GVV_OK; }
+  if (!strcmp(key, "bwd_persistent")) { h->bwdPersistent = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "exp")) { h->exp = value; return GVV_OK; }
   if (!strcmp(key, "chain")) { h->chain = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "resolve_prefetch")) { h->resolvePrefetch = value ? 1 : 0; return GVV_OK; }
@@ -367,7 +369,7 @@ extern "C" int gvv_backward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
 
   BwdArgs a;
   a.B = B; a.C = h->C; a.N = h->N; a.F = h->F; a.W = h->W; a.H = h->H; a.texH = texH; a.texW = texW;
-  a.albedo = h->albedo; a.shading = h->shading; a.imgFilter = h->imgFilter; a.texBilinear = h->texBilinear; a.chain = h->chain && !h->timer.enabled; a.sharedBatch = h->sharedBatchGrads; a.exp = h->exp; a.target_du = h->targetDu; a.target_dv = h->targetDv;
+  a.albedo = h->albedo; a.shading = h->shading; a.imgFilter = h->imgFilter; a.texBilinear = h->texBilinear; a.chain = h->chain && !h->timer.enabled; a.sharedBatch = h->sharedBatchGrads; a.exp = h->exp; a.bwdPersistent = h->bwdPersistent; a.ctaSlots = h->ctaSlots; a.target_du = h->targetDu; a.target_dv = h->targetDv;
   a.render_grad = render_grad; a.target_grad = target_grad; a.vertex_pos = vertex_pos; a.vertex_color = vertex_color;
   a.texture = texture; a.sh_coeff = sh_coeff; a.target_image = target_image; a.vertex_normal = vertex_normal;
   a.bary = bary; a.extrinsics = extrinsics; a.intrinsics = intrinsics; a.texcoords = h->texcoords;

@@ -17,6 +17,7 @@
 //                        factor q, so we scatter Gn[v_i] += bcc_i*q per pixel and apply the
 //                        cross-product Jacobians (RendererUtil.h:422-539) once per TRIANGLE here
 //                        (9 atomics per triangle that received any gradient) -- same mathematics.
+#include <algorithm>
 #include "gvv_internal.h"
 
 namespace gvv {
@@ -94,7 +95,7 @@ __device__ __forceinline__ void bary_vjp_fast(V3 o, V3 d, V3 v0, V3 v1, V3 v2, f
 
 __device__ __forceinline__ V3 ld4(const float4* __restrict__ p, size_t i) { const float4 v = __ldg(p + i); return v3(v.x, v.y, v.z); }
 
-// mbarrier + bulk async copy (TMA) helpers for the staged input tile of pixel_grad_kernel
+// mbarrier + bulk async copy (TMA) helpers for the face-tile ring of pixel_grad_persistent_kernel
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
@@ -121,85 +122,18 @@ constexpr int kSlabs = 4;
 // SHADED is a template parameter: the shaded instance is the full chain; the shadeless one drops, at compile time,
 // everything its gradients do not depend on (SH basis and light, the albedo VALUE and its texel / colour gathers,
 // the shading-normal position term and its buffers), which the register allocator could not do behind a runtime flag.
-template <bool SHADED, int ALBEDO, bool STAGED>
-__global__ void __launch_bounds__(256, 3)
-pixel_grad_kernel(const PixelParams p) {
-  chain_wait(); chain_trigger();
-  extern __shared__ __align__(16) float buf_dyn[];   // per warp: (kVals + kShRows + kIdRows) rows, value-major, kRow floats per value (32 pixels + pad)
-  __shared__ float shPart[8][kVals];
-  __shared__ CamRec cam;        // only staged for the model-to-data term (K, E)
-  // The per-view constants are laid out for 128-bit broadcast reads: the kernel was bound by the L1 data pipe
-  // (l1tex__data_pipe_lsu_wavefronts 79 % of peak, profiles/r02_ncu_summaries.md), where a scalar LDS costs a
-  // wavefront like a 128-bit one: 9 instead of 51 reads per pixel for the SH coefficients, 4 instead of 15 for the ray.
-  __shared__ float4 shc4[9];    // channel ch: coefficients 0..8 in shc4[3 ch .. 3 ch + 2] (three pad words)
-  __shared__ float4 camv[4];    // rows 0..2 of (K E)^-1, ray origin
-
-  const int view = blockIdx.z, b = (int)(((float)view + 0.5f) * p.invC);   // = view / C without the integer division (exact below 2^22 views)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int x = blockIdx.x * 32 + lane;
-  const size_t viewBase = (size_t)view * p.W * p.H;
-  // STAGED (off: measured slower, 0.214 -> 0.245 ms): the tile's inputs (face 4 KB, then -- only when something is visible -- bary 8 KB + render_grad 12 KB)
-  // arrive by bulk async copies (TMA), one 128 / 256 / 384-byte row per copy, completion on two mbarriers: the
-  // first hop of the face -> triangle -> vertices chain is off every warp's critical path and the per-pixel
-  // loads (two of them at a 12-byte stride) become shared-memory reads.  Border tiles and unaligned images
-  // keep the direct loads.
-  __shared__ __align__(8) unsigned long long mbar[2];
-  int* sFace = reinterpret_cast<int*>(buf_dyn + 8 * kWarpBufFloats);
-  float2* sBary = reinterpret_cast<float2*>(sFace + 1024);
-  float* sRg = reinterpret_cast<float*>(sBary + 1024);
-  const bool staged = STAGED && ((p.W & 3) == 0) && (int)blockIdx.x * 32 + 32 <= p.W && (int)blockIdx.y * 32 + 32 <= p.H &&
-                      ((reinterpret_cast<uintptr_t>(p.face) | reinterpret_cast<uintptr_t>(p.bary) | reinterpret_cast<uintptr_t>(p.render_grad)) & 15) == 0;
-  const size_t tileRow0 = viewBase + (size_t)(blockIdx.y * 32) * p.W + blockIdx.x * 32;   // first pixel of row 0 of the tile
-  bool any = false;
-  if (staged) {
-    if (tid == 0) { mbar_init(&mbar[0], 32); mbar_init(&mbar[1], 32); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    __syncthreads();
-    if (tid < 32) { mbar_expect_tx(&mbar[0], 128); bulk_load(sFace + tid * 32, p.face + tileRow0 + (size_t)tid * p.W, 128, &mbar[0]); }
-  } else {
-#pragma unroll
-    for (int s = 0; s < kSlabs; ++s) {
-      const int ys = blockIdx.y * 32 + s * 8 + warp;
-      const int f = (x < p.W && ys < p.H) ? __ldg(p.face + viewBase + (size_t)ys * p.W + x) : -1;
-      any = any || f >= 0;
-    }
-  }
+// One 32-pixel scanline segment of one warp: per-pixel chain, run-aggregated scatter, SH partial sums (shsum: lane j < 27
+// holds the running sum of SH gradient (ch,k) = (j / 9, j % 9)).  Shared by the one-tile-per-CTA and the persistent kernel.
+template <bool SHADED, int ALBEDO>
+__device__ __forceinline__ void segment_grad(const PixelParams& p, const CamRec& cam, const float4* __restrict__ shc4, const float4* __restrict__ camv,
+                                             float* __restrict__ mybuf, const int lane, const int view, const int b, const int x, const int y,
+                                             const size_t pix, const int face, float& shsum) {
   constexpr bool shaded = SHADED;
   constexpr int albedo = ALBEDO;       // vertexColor | textured | foregroundMask (the other modes have no gradient)
-
-  // camera + SH staging overlaps the latency of the face loads; ONE barrier publishes both and
-  // tells whether anything is visible in this 32x32 tile
-  if (tid < 64) { if (p.target_grad) reinterpret_cast<float*>(&cam)[tid] = __ldg(reinterpret_cast<const float*>(p.cams + view) + tid); }
-  else if (tid < 64 + 36) { const int i = tid - 64, ch = i / 12, k = i - 12 * ch; reinterpret_cast<float*>(shc4)[i] = k < 9 ? __ldg(p.sh_coeff + (size_t)view * 27 + ch * 9 + k) : 0.f; }
-  else if (tid >= 128 && tid < 128 + 16) {
-    const int i = tid - 128;
-    const CamRec* cr = p.cams + view;
-    reinterpret_cast<float*>(camv)[i] = i < 12 ? __ldg(cr->Pinv + i) : (i < 15 ? __ldg(cr->ro + (i - 12)) : 0.f);
-  }
-  if (staged) {
-    mbar_wait(&mbar[0], 0);
-#pragma unroll
-    for (int s = 0; s < kSlabs; ++s) any = any || sFace[(s * 8 + warp) * 32 + lane] >= 0;
-  }
-  if (__syncthreads_or(any) == 0) return;
-  if (staged && tid < 32) {
-    mbar_expect_tx(&mbar[1], 640);
-    bulk_load(sBary + tid * 32, p.bary + 2 * (tileRow0 + (size_t)tid * p.W), 256, &mbar[1]);
-    bulk_load(sRg + tid * 96, p.render_grad + 3 * (tileRow0 + (size_t)tid * p.W), 384, &mbar[1]);
-  }
-
-  float* mybuf = buf_dyn + warp * kWarpBufFloats;
   float* mine = mybuf + lane;   // value j of this lane's pixel lives at mine[j * kRow]
-  float shsum = 0.f;            // lane j < 27: SH gradient (ch,k) summed over this warp's segments
-
-#pragma unroll 1
-  for (int slab = 0; slab < kSlabs; ++slab) {
-  const int y = blockIdx.y * 32 + slab * 8 + warp;
-  const size_t pix = viewBase + (size_t)y * p.W + x;
-  const int spix = (slab * 8 + warp) * 32 + lane;                          // pixel index inside the staged tile
-  const int face = staged ? sFace[spix] : ((x < p.W && y < p.H) ? __ldg(p.face + pix) : -1);      // (not staged: second read of the line: L1/L2 hit)
   const bool covered = face >= 0;
   const unsigned cv = __ballot_sync(FULL_MASK, covered);
-  if (cv == 0) continue;
+  if (cv == 0) return;
   float gA[3] = {0.f, 0.f, 0.f};
   float Y[9];
 #pragma unroll
@@ -214,8 +148,7 @@ pixel_grad_kernel(const PixelParams p) {
       const F3 rdx = ray_dir_exact(Pv, rov, (float)x + 0.5f, (float)y + 0.5f);
       const V3 d = v3(rdx.x, rdx.y, rdx.z), o = v3(ro4.x, ro4.y, ro4.z);
       const int4 fc = __ldg(p.faces4 + face);
-      if (staged) mbar_wait(&mbar[1], 0);      // bary + render_grad of the tile have landed (immediate after the first time)
-      const float2 ab = staged ? sBary[spix] : __ldg(reinterpret_cast<const float2*>(p.bary) + pix);
+      const float2 ab = __ldg(reinterpret_cast<const float2*>(p.bary) + pix);
       const float bc[3] = {ab.x, ab.y, 1.f - ab.x - ab.y};
       mine[(kVals + kShRows + 0) * kRow] = __int_as_float(fc.x);   // vertex ids for the run-end atomics of the scatter stage
       mine[(kVals + kShRows + 1) * kRow] = __int_as_float(fc.y);
@@ -252,8 +185,7 @@ pixel_grad_kernel(const PixelParams p) {
                       sc[1] + sc[4] * n.x + sc[5] * n.z + sc[8] * -2.f * n.y,
                       sc[2] + sc[5] * n.y + sc[6] * 6.f * n.z + sc[7] * n.x);
       }
-      const float3 g = staged ? make_float3(sRg[3 * spix], sRg[3 * spix + 1], sRg[3 * spix + 2])
-                              : make_float3(__ldg(p.render_grad + 3 * pix), __ldg(p.render_grad + 3 * pix + 1), __ldg(p.render_grad + 3 * pix + 2));
+      const float3 g = make_float3(__ldg(p.render_grad + 3 * pix), __ldg(p.render_grad + 3 * pix + 1), __ldg(p.render_grad + 3 * pix + 2));
       const float gl[3] = {shaded ? g.x * light[0] : g.x, shaded ? g.y * light[1] : g.y, shaded ? g.z * light[2] : g.z};
 
       // ---- albedo (:242-319) and its gradients (:327-395) ----
@@ -445,17 +377,157 @@ pixel_grad_kernel(const PixelParams p) {
     }
     __syncwarp();
   }
-  }   // slab
+}
+
+// The per-view constants of both kernels are laid out for 128-bit broadcast reads: the kernel was bound by the L1 data
+// pipe (l1tex__data_pipe_lsu_wavefronts 79 % of peak, profiles/r02_ncu_summaries.md), where a scalar LDS costs a
+// wavefront like a 128-bit one: 9 instead of 51 reads per pixel for the SH coefficients, 4 instead of 15 for the ray.
+//   shc4[9]: channel ch has its coefficients 0..8 in shc4[3 ch .. 3 ch + 2] (three pad words); camv[4]: rows 0..2 of (K E)^-1, ray origin
+__device__ __forceinline__ void stage_view_constants(const PixelParams& p, int view, int t, CamRec* cam, float4* shc4, float4* camv) {
+  // t = thread index within a group of >= 144 threads
+  if (t < 64) { if (p.target_grad) reinterpret_cast<float*>(cam)[t] = __ldg(reinterpret_cast<const float*>(p.cams + view) + t); }   // K, E: model-to-data term only
+  else if (t < 64 + 36) { const int i = t - 64, ch = i / 12, k = i - 12 * ch; reinterpret_cast<float*>(shc4)[i] = k < 9 ? __ldg(p.sh_coeff + (size_t)view * 27 + ch * 9 + k) : 0.f; }
+  else if (t >= 128 && t < 128 + 16) {
+    const int i = t - 128;
+    const CamRec* cr = p.cams + view;
+    reinterpret_cast<float*>(camv)[i] = i < 12 ? __ldg(cr->Pinv + i) : (i < 15 ? __ldg(cr->ro + (i - 12)) : 0.f);
+  }
+}
+
+// One 32x32 tile per CTA (any image size).  80 registers, 3 CTAs/SM: at 64 registers (4 CTAs/SM) the per-pixel chain
+// spilled ~90 bytes in its hot path -- local-memory traffic through the same L1 data pipe that bounds the kernel.
+template <bool SHADED, int ALBEDO>
+__global__ void __launch_bounds__(256, 3)
+pixel_grad_kernel(const PixelParams p) {
+  chain_wait(); chain_trigger();
+  extern __shared__ __align__(16) float buf_dyn[];   // per warp: (kVals + kShRows + kIdRows) rows, value-major, kRow floats per value (32 pixels + pad)
+  __shared__ float shPart[8][kVals];
+  __shared__ CamRec cam;
+  __shared__ float4 shc4[9];
+  __shared__ float4 camv[4];
+
+  const int view = blockIdx.z, b = (int)(((float)view + 0.5f) * p.invC);   // = view / C without the integer division (exact below 2^22 views)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x = blockIdx.x * 32 + lane;
+  const size_t viewBase = (size_t)view * p.W * p.H;
+  bool any = false;
+#pragma unroll
+  for (int s = 0; s < kSlabs; ++s) {
+    const int ys = blockIdx.y * 32 + s * 8 + warp;
+    const int f = (x < p.W && ys < p.H) ? __ldg(p.face + viewBase + (size_t)ys * p.W + x) : -1;
+    any = any || f >= 0;
+  }
+  // constant staging overlaps the latency of the face loads; ONE barrier publishes it and
+  // tells whether anything is visible in this 32x32 tile
+  stage_view_constants(p, view, tid, &cam, shc4, camv);
+  if (__syncthreads_or(any) == 0) return;
+
+  float* mybuf = buf_dyn + warp * kWarpBufFloats;
+  float shsum = 0.f;            // lane j < 27: SH gradient (ch,k) summed over this warp's segments
+#pragma unroll 1
+  for (int slab = 0; slab < kSlabs; ++slab) {
+    const int y = blockIdx.y * 32 + slab * 8 + warp;
+    const size_t pix = viewBase + (size_t)y * p.W + x;
+    const int face = (x < p.W && y < p.H) ? __ldg(p.face + pix) : -1;      // second read of the line: L1/L2 hit
+    segment_grad<SHADED, ALBEDO>(p, cam, shc4, camv, mybuf, lane, view, b, x, y, pix, face, shsum);
+  }
 
   // warp -> block -> 27 atomics per tile
   if (lane < kVals) shPart[warp][lane] = shsum;
   __syncthreads();
-  if (shaded && tid < kVals) {
+  if (SHADED && tid < kVals) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += shPart[w][tid];
     if (s != 0.f) atomicAdd(p.sh_grad + (size_t)(p.sharedBatch ? view - b * p.C : view) * 27 + tid, s);
   }
+}
+
+// Persistent variant for images made of whole tiles (W, H multiples of 32, 16-byte aligned face buffer): one CTA per
+// resident slot, each pulling 32x32 tiles (view-major order) from a global counter.  The 4 KB face tile -- the first
+// hop of the face -> triangle -> vertices chain, and all an empty tile (40 % of them at 50 % coverage) ever needs --
+// arrives by bulk async copies (TMA, one 128-byte row per copy) into a ring of kFaceRing shared-memory buffers, each
+// with its mbarrier, issued kFaceRing tiles ahead (a slot is refilled as soon as its face ids sit in registers): the
+// load latency and the per-CTA prologue (launch, constants) that the one-tile-per-CTA kernel pays 1024 times per view
+// are off the critical path.  Per-view constants are double-buffered (a warp may enter the next view's first tile
+// while another still finishes the previous one), SH partial sums stay in registers until the view changes.
+constexpr int kFaceRing = 4;
+
+template <bool SHADED, int ALBEDO>
+__global__ void __launch_bounds__(256, 3)
+pixel_grad_persistent_kernel(const PixelParams p, int* __restrict__ tileCounter, int tilesX, int tilesPerView, int totalTiles) {
+  chain_wait(); chain_trigger();
+  extern __shared__ __align__(16) float buf_dyn[];
+  __shared__ CamRec cam[2];
+  __shared__ float4 shc4[2][9];
+  __shared__ float4 camv[2][4];
+  __shared__ __align__(8) unsigned long long mbar[kFaceRing];
+  __shared__ int ringTile[kFaceRing];
+  int* sFace = reinterpret_cast<int*>(buf_dyn + 8 * kWarpBufFloats);      // kFaceRing tiles of 1024 face ids
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* mybuf = buf_dyn + warp * kWarpBufFloats;
+  // tile t of the ring slot s: 32 rows of 128 bytes, one bulk copy per lane of warp 0
+  auto issue = [&](int t, int s) {
+    const int view = t / tilesPerView, r = t - view * tilesPerView, ty = r / tilesX, tx = r - ty * tilesX;
+    const int32_t* src = p.face + (size_t)view * p.W * p.H + (size_t)(ty * 32 + lane) * p.W + tx * 32;
+    mbar_expect_tx(&mbar[s], 128);
+    bulk_load(sFace + s * 1024 + lane * 32, src, 128, &mbar[s]);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kFaceRing; ++s) mbar_init(&mbar[s], 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    ringTile[0] = blockIdx.x;                                   // the first tile is static, the rest comes from the counter
+#pragma unroll
+    for (int s = 1; s < kFaceRing; ++s) ringTile[s] = atomicAdd(tileCounter, 1);
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int s = 0; s < kFaceRing; ++s) if (ringTile[s] < totalTiles) issue(ringTile[s], s);
+  }
+  int curView = -1, b = 0, cs = 0;      // cs: constant slot, toggled at every view change (consecutive tiles of a CTA may be several views apart)
+  float shsum = 0.f;
+  auto flush_sh = [&]() {
+    if (SHADED && lane < kVals && shsum != 0.f) atomicAdd(p.sh_grad + (size_t)(p.sharedBatch ? curView - b * p.C : curView) * 27 + lane, shsum);
+    shsum = 0.f;
+  };
+#pragma unroll 1
+  for (int it = 0;; ++it) {
+    const int s = it % kFaceRing;
+    const int tile = ringTile[s];
+    if (tile >= totalTiles) break;                              // the counter only grows: every later slot is past the end too
+    const int view = tile / tilesPerView, r = tile - view * tilesPerView, ty = r / tilesX, tx = r - ty * tilesX;
+    if (view != curView) {
+      if (curView >= 0) flush_sh();
+      curView = view; b = (int)(((float)view + 0.5f) * p.invC); cs ^= 1;
+      stage_view_constants(p, view, tid, &cam[cs], shc4[cs], camv[cs]);   // every thread sees the change at the same tile; published by the barrier below
+    }
+    mbar_wait(&mbar[s], (it / kFaceRing) & 1);
+    const int* tf = sFace + s * 1024;
+    int f4[kSlabs];
+    bool any = false;
+#pragma unroll
+    for (int sl = 0; sl < kSlabs; ++sl) { f4[sl] = tf[(sl * 8 + warp) * 32 + lane]; any = any || f4[sl] >= 0; }
+    const int busy = __syncthreads_or(any);     // every thread holds its face ids (and the tile id) in registers: the slot is refilled right away
+    if (warp == 0) {
+      int tn = 0;
+      if (lane == 0) { tn = atomicAdd(tileCounter, 1); ringTile[s] = tn; }      // read again kFaceRing iterations (barriers) later
+      tn = __shfl_sync(FULL_MASK, tn, 0);
+      if (tn < totalTiles) issue(tn, s);
+    }
+    if (!busy) continue;
+    const int x = tx * 32 + lane;
+    const size_t viewBase = (size_t)view * p.W * p.H;
+#pragma unroll 1
+    for (int sl = 0; sl < kSlabs; ++sl) {
+      const int y = ty * 32 + sl * 8 + warp;
+      const int face = sl == 0 ? f4[0] : (sl == 1 ? f4[1] : (sl == 2 ? f4[2] : f4[3]));
+      segment_grad<SHADED, ALBEDO>(p, cam[cs], shc4[cs], camv[cs], mybuf, lane, view, b, x, y, viewBase + (size_t)y * p.W + x, face, shsum);
+    }
+  }
+  if (curView >= 0) flush_sh();
 }
 
 // Repack of the caller's 12-byte AoS vertex arrays into aligned float4 (one 16-B gather instead of
@@ -468,6 +540,7 @@ struct PrepArgs {
   const float *extr, *intr;
   CamRec* cams;
   int V;
+  int* tileCounter; int counterInit;   // work counter of pixel_grad_persistent_kernel: the first gridDim.x tiles are static
 };
 
 __global__ void prep_kernel(PrepArgs a) {
@@ -475,6 +548,7 @@ __global__ void prep_kernel(PrepArgs a) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t0 < a.V) fill_camrec(a.extr, a.intr, a.cams, (int)t0);   // camera records for pixel_grad_kernel (ref :17-61)
+  if (t0 == 0 && a.tileCounter) *a.tileCounter = a.counterInit;
   for (long long i = t0; i < a.nBN; i += stride) {
     a.pos4[i] = make_float4(__ldg(a.vertex_pos + 3 * i), __ldg(a.vertex_pos + 3 * i + 1), __ldg(a.vertex_pos + 3 * i + 2), 0.f);
     if (a.vertex_color) a.col4[i] = make_float4(__ldg(a.vertex_color + 3 * i), __ldg(a.vertex_color + 3 * i + 1), __ldg(a.vertex_color + 3 * i + 2), 0.f);
@@ -562,6 +636,11 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   pa.pos4 = a.s.bpos4; pa.col4 = a.s.bcol4; pa.nor4 = a.s.bnor4;
   pa.nBN = (long long)a.B * a.N; pa.nVN = (long long)V * a.N;
   pa.extr = a.extrinsics; pa.intr = a.intrinsics; pa.cams = a.s.cams; pa.V = V;
+  // persistent kernel: whole-tile images only (the bulk copies need 16-byte aligned 128-byte rows)
+  const bool persistent = a.bwdPersistent && (a.W % 32) == 0 && (a.H % 32) == 0 && (reinterpret_cast<uintptr_t>(a.face) & 15) == 0;
+  const int tilesX = a.W / 32, tilesPerView = tilesX * (a.H / 32), totalTiles = tilesPerView * V;
+  const int pgCtas = std::min(totalTiles, std::max(1, a.ctaSlots / 4 * 3));     // 3 resident CTAs per SM
+  pa.tileCounter = a.s.tileCounter; pa.counterInit = pgCtas;
   tm->begin(K_ZERO, st);
   launch_chained(a.chain, prep_kernel, dim3(148 * 8), dim3(256), 0, st, pa);
   tm->end(st);
@@ -577,17 +656,19 @@ int launch_backward(const BwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   tm->begin(K_PIXEL_GRAD, st);
   constexpr int kPixelSmem = 8 * kWarpBufFloats * (int)sizeof(float);
   const dim3 pgGrid((a.W + 31) / 32, (a.H + 31) / 32, V);
-#define GVV_PG2(S, A, ST) do { static unsigned long long attr = 0; \
-    constexpr int smem = kPixelSmem + ((ST) ? 24576 : 0); \
-    if (first_use_on_device(&attr)) cudaFuncSetAttribute(pixel_grad_kernel<S, A, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-    launch_chained(a.chain, pixel_grad_kernel<S, A, ST>, pgGrid, dim3(256), smem, st, p); } while (0)
-#define GVV_PG(S, A) do { if (a.exp & 16) GVV_PG2(S, A, true); else GVV_PG2(S, A, false); } while (0)
+#define GVV_PG(S, A) do { static unsigned long long attr = 0, attrP = 0; \
+    if (persistent) { \
+      constexpr int smemP = kPixelSmem + kFaceRing * 4096; \
+      if (first_use_on_device(&attrP)) cudaFuncSetAttribute(pixel_grad_persistent_kernel<S, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemP); \
+      launch_chained(a.chain, pixel_grad_persistent_kernel<S, A>, dim3(pgCtas), dim3(256), smemP, st, p, a.s.tileCounter, tilesX, tilesPerView, totalTiles); \
+    } else { \
+      if (first_use_on_device(&attr)) cudaFuncSetAttribute(pixel_grad_kernel<S, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPixelSmem); \
+      launch_chained(a.chain, pixel_grad_kernel<S, A>, pgGrid, dim3(256), kPixelSmem, st, p); } } while (0)
   const bool sh = a.shading == GVV_SHADING_SHADED;
   if (a.albedo == GVV_ALBEDO_VERTEX_COLOR) { if (sh) GVV_PG(true, GVV_ALBEDO_VERTEX_COLOR); else GVV_PG(false, GVV_ALBEDO_VERTEX_COLOR); }
   else if (a.albedo == GVV_ALBEDO_TEXTURED) { if (sh) GVV_PG(true, GVV_ALBEDO_TEXTURED); else GVV_PG(false, GVV_ALBEDO_TEXTURED); }
   else { if (sh) GVV_PG(true, GVV_ALBEDO_FOREGROUND_MASK); else GVV_PG(false, GVV_ALBEDO_FOREGROUND_MASK); }   // foregroundMask (and any mode without an albedo gradient)
 #undef GVV_PG
-#undef GVV_PG2
   tm->end(st);
   ++launches;
   const bool fusedAR = a.ar.blocks > 0 && !a.arAfter;

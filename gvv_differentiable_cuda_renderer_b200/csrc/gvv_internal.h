@@ -39,6 +39,7 @@ struct Scratch {
   float4* bpos4 = nullptr;       // [B*N]  backward: repacked vertex_pos (raw)
   float4* bcol4 = nullptr;       // [B*N]  backward: repacked vertex_color
   float4* bnor4 = nullptr;       // [V*N]  backward: repacked vertex_normal input
+  int* tileCounter = nullptr;    // [1]    backward: work counter of the persistent pixel-gradient kernel, set by prep_kernel
   unsigned long long* ctaTrace = nullptr;   // [V*nT*4] debug (option cta_trace): globaltimer start, end, bin size, SM id per raster CTA
 };
 
@@ -85,6 +86,7 @@ struct gvv_renderer {
   int interleave = 1;         // raster: batch j takes bin entries j, j+nBatches, ... instead of a contiguous chunk
   int ctaThreads = 256;       // raster: threads per tile CTA (256 | 128)
   int batchDiv = 8;           // raster: a bin of n triangles is cut into batches of ceil(n / batchDiv) (<= 32) triangles
+  int bwdPersistent = 0;      // (measured slower: 0.272 vs 0.218 ms) backward: persistent pixel-gradient kernel with a TMA face-tile ring (whole-tile images); 0 = one tile per CTA
   int exp = 0;                // development: bit mask of experimental code paths under A/B measurement (tools/gpu_ab.py); 0 in production
   int rayCache = 0;           // raster: 1 = per-pixel ray cache in shared memory (3 CTAs/SM), 0 = recompute (4 CTAs/SM, measured faster)
   float cullMargin = 0.0625f; // px (fixed part of the margin); < 0 disables the conservative screen-space pre-test
@@ -117,7 +119,7 @@ struct FwdArgs {
 };
 
 struct BwdArgs {
-  int B, C, N, F, W, H, texH, texW, albedo, shading, imgFilter, texBilinear, chain, sharedBatch, exp;
+  int B, C, N, F, W, H, texH, texW, albedo, shading, imgFilter, texBilinear, chain, sharedBatch, exp, bwdPersistent, ctaSlots;
   const float *render_grad, *target_grad, *vertex_pos, *vertex_color, *texture, *sh_coeff, *target_image,
       *vertex_normal, *bary, *extrinsics, *intrinsics, *texcoords, *target_du, *target_dv;
   const int32_t* face;
