@@ -13,7 +13,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libgvv_b200.so")
+LIB_PATH = os.environ.get("GVV_B200_LIB") or os.path.join(_PKG, "libgvv_b200.so")   # (the override serves A/B builds of the library, tools/build_variants.sh)
 CSRC = os.path.join(_PKG, "csrc")
 SOURCES = ["gvv_api.cu", "gvv_forward.cu", "gvv_backward.cu", "gvv_normalmap.cu", "gvv_helpers.cu", "gvv_microbench.cu"]
 

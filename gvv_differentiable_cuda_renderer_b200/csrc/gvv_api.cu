@@ -255,7 +255,7 @@ extern "C" int gvv_set_option(gvv_handle h, const char* key, int32_t value) {
   if (!strcmp(key, "shared_batch_grads")) { h->sharedBatchGrads = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "texture_bilinear")) { h->texBilinear = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "bwd_persistent")) { h->bwdPersistent = value ? 1 : 0; return GVV_OK; }
-  if (!strcmp(key, "exp")) { h->exp = value; return GVV_OK; }
+  if (!strcmp(key, "bulk_out")) { h->bulkOut = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "chain")) { h->chain = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "resolve_prefetch")) { h->resolvePrefetch = value ? 1 : 0; return GVV_OK; }
   if (!strcmp(key, "spread_empty")) { h->spreadEmpty = value ? 1 : 0; return GVV_OK; }
@@ -307,7 +307,7 @@ extern "C" int gvv_forward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
   FwdArgs a;
   a.B = B; a.C = h->C; a.N = h->N; a.F = h->F; a.W = h->W; a.H = h->H; a.texH = texH; a.texW = texW;
   a.albedo = h->albedo; a.shading = h->shading;
-  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin; a.rayCache = h->rayCache; a.batchDiv = h->batchDiv; a.ctaThreads = h->ctaThreads; a.interleave = h->interleave; a.hiz = h->hiz; a.hizMin = h->hizMin; a.spanZ = h->spanZ; a.splitUnit = h->splitUnit; a.heavyThr = h->heavyThr; a.heavySlots = h->heavySlots; a.heavyMode = h->heavyMode; a.ctaSlots = h->ctaSlots; a.spreadEmpty = h->spreadEmpty; a.texBilinear = h->texBilinear; a.resolvePrefetch = h->resolvePrefetch; a.exp = h->exp; a.chain = h->chain && !h->timer.enabled;   // per-kernel timing wants plain stream order
+  a.tile = h->tile; a.tilesX = h->tilesX; a.tilesY = h->tilesY; a.nT = h->nT; a.cullMargin = h->cullMargin; a.rayCache = h->rayCache; a.batchDiv = h->batchDiv; a.ctaThreads = h->ctaThreads; a.interleave = h->interleave; a.hiz = h->hiz; a.hizMin = h->hizMin; a.spanZ = h->spanZ; a.splitUnit = h->splitUnit; a.heavyThr = h->heavyThr; a.heavySlots = h->heavySlots; a.heavyMode = h->heavyMode; a.ctaSlots = h->ctaSlots; a.spreadEmpty = h->spreadEmpty; a.texBilinear = h->texBilinear; a.resolvePrefetch = h->resolvePrefetch; a.bulkOut = h->bulkOut; a.chain = h->chain && !h->timer.enabled;   // per-kernel timing wants plain stream order
   a.vertex_pos = vertex_pos; a.vertex_color = vertex_color; a.texture = texture; a.sh_coeff = sh_coeff;
   a.extrinsics = extrinsics; a.intrinsics = intrinsics; a.texcoords = h->texcoords;
   a.faces4 = h->faces4; a.vfOffsets = h->vfOffsets; a.vfList = h->vfList;
@@ -369,7 +369,7 @@ extern "C" int gvv_backward(gvv_handle h, int32_t B, int32_t texH, int32_t texW,
 
   BwdArgs a;
   a.B = B; a.C = h->C; a.N = h->N; a.F = h->F; a.W = h->W; a.H = h->H; a.texH = texH; a.texW = texW;
-  a.albedo = h->albedo; a.shading = h->shading; a.imgFilter = h->imgFilter; a.texBilinear = h->texBilinear; a.chain = h->chain && !h->timer.enabled; a.sharedBatch = h->sharedBatchGrads; a.exp = h->exp; a.bwdPersistent = h->bwdPersistent; a.ctaSlots = h->ctaSlots; a.target_du = h->targetDu; a.target_dv = h->targetDv;
+  a.albedo = h->albedo; a.shading = h->shading; a.imgFilter = h->imgFilter; a.texBilinear = h->texBilinear; a.chain = h->chain && !h->timer.enabled; a.sharedBatch = h->sharedBatchGrads; a.bwdPersistent = h->bwdPersistent; a.ctaSlots = h->ctaSlots; a.target_du = h->targetDu; a.target_dv = h->targetDv;
   a.render_grad = render_grad; a.target_grad = target_grad; a.vertex_pos = vertex_pos; a.vertex_color = vertex_color;
   a.texture = texture; a.sh_coeff = sh_coeff; a.target_image = target_image; a.vertex_normal = vertex_normal;
   a.bary = bary; a.extrinsics = extrinsics; a.intrinsics = intrinsics; a.texcoords = h->texcoords;

@@ -523,8 +523,8 @@ struct RasterParams {
   const float* texture; const float* texcoords; const float* sh_coeff;
   float* bary; int32_t* face; float* render;
   unsigned long long* ctaTrace;
-  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, hizMin, spanZ, role, pdl, grid2d, texBilinear, resolvePrefetch, exp;
-  float cullMargin;
+  int C, N, F, W, H, texH, texW, albedo, shading, tilesX, nT, nItems, V, batchDiv, interleave, hiz, hizMin, spanZ, role, pdl, grid2d, texBilinear, resolvePrefetch, bulkOut;
+  float cullMargin, invC;
 };
 
 __device__ __forceinline__ TriSetup load_setup(const RasterParams& p, int b, int view, int4 fc, F3 ros,
@@ -582,8 +582,8 @@ constexpr int kWarpSmemBytes = kBatch * (int)sizeof(TriRec) + kBatch * (int)size
 template <int TS, bool RC, int NTH>
 constexpr int raster_smem_bytes() { return TS * TS * (16 + (RC ? 12 : 0)) + (NTH / 32) * kWarpSmemBytes; }
 
-template <int TS, bool RC, int NTH, int OCC = (RC ? 3 : 4)>
-__global__ void __launch_bounds__(NTH, OCC * (256 / NTH))
+template <int TS, bool RC, int NTH>
+__global__ void __launch_bounds__(NTH, (RC ? 3 : 4) * (256 / NTH))
 raster_kernel(const RasterParams p) {
   constexpr int NPIX = TS * TS;
   constexpr int ZRAY = NPIX * (16 + (RC ? 12 : 0));
@@ -596,6 +596,7 @@ raster_kernel(const RasterParams p) {
   __shared__ CamRec cam;
   __shared__ int nextBatch;
   __shared__ unsigned sZmax;
+  __shared__ int sPlan[2];      // batch size and batch count of the current pass: two integer divisions by run-time values, done by ONE thread
 
   // Grid (V, items): x = view runs fastest, so the heaviest work items of every view are scheduled first
   // (1-D fallback with a division when the work list is longer than gridDim.y allows).
@@ -616,7 +617,7 @@ raster_kernel(const RasterParams p) {
   const int tileX = item & 0xfff, tileY = (item >> 12) & 0xfff, tile = tileY * p.tilesX + tileX;
   const int stripLog = (item >> 27) & 3, rowN = TS >> stripLog, rowLo = ((item >> 24) & 7) * rowN;
   const int qLo = rowLo * TS, qHi = (rowLo + rowN) * TS;
-  const int b = view / p.C;
+  const int b = (int)(((float)view + 0.5f) * p.invC);   // = view / C without the integer division (exact below 2^22 views)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tileX0 = tileX * TS, tileY0 = tileY * TS;
   const size_t tidx = (size_t)view * p.nT + tile;
@@ -669,7 +670,14 @@ raster_kernel(const RasterParams p) {
 
   if (tid < 64) reinterpret_cast<float*>(&cam)[tid] = reinterpret_cast<const float*>(p.cams + view)[tid];
   if (tid >= 64 && tid < 64 + 27) shc[tid - 64] = p.sh_coeff[(size_t)view * 27 + (tid - 64)];
-  if (tid == 96) { nextBatch = 0; sZmax = 0u; }
+  const int nNear = p.tileCursor[tidx];
+  const bool twoPass = p.hiz && cntSmall + cntBig >= p.hizMin && nNear < cntSmall;
+  if (tid == 96) {
+    nextBatch = 0; sZmax = 0u;
+    const int nPass0 = (twoPass ? nNear : cntSmall) + cntBig;
+    const int G0 = min(kBatch, max(1, (nPass0 + p.batchDiv - 1) / p.batchDiv));
+    sPlan[0] = G0; sPlan[1] = (nPass0 + G0 - 1) / G0;
+  }
   __syncthreads();
   const F3 ros = mk3(cam.ros[0], cam.ros[1], cam.ros[2]);
 
@@ -738,8 +746,6 @@ raster_kernel(const RasterParams p) {
   // EVERY pixel of the (by then fully covered) z-tile is dropped before any of its rows is touched.  Keys only
   // ever decrease, so such a triangle can win no pixel: the result is bit-identical (hiz = 0 and short bins
   // rasterise everything in one pass). ----
-  const int nNear = p.tileCursor[tidx];
-  const bool twoPass = p.hiz && cntAll >= p.hizMin && nNear < cntSmall;
   for (int pass = 0; pass < 2; ++pass) {
   unsigned zmaxBits = 0xffffffffu;                    // pass 1: farthest current winner of the tile (0xffffffff if a pixel is still empty)
   if (pass == 1) {
@@ -757,15 +763,20 @@ raster_kernel(const RasterParams p) {
     }
     m = __reduce_max_sync(FULL_MASK, m);
     if (lane == 0) atomicMax(&sZmax, m);
-    if (tid == 0) nextBatch = 0;
+    if (tid == 0) {
+      nextBatch = 0;
+      const int nPass1 = cntSmall - nNear;
+      const int G1 = min(kBatch, max(1, (nPass1 + p.batchDiv - 1) / p.batchDiv));
+      sPlan[0] = G1; sPlan[1] = (nPass1 + G1 - 1) / G1;      // (every thread read the pass-0 plan before the barrier above)
+    }
     __syncthreads();
     zmaxBits = sZmax;
   }
   const int passLo = pass == 0 ? 0 : nNear;                                     // first bin entry of this pass
   const int nSmall = pass == 0 ? (twoPass ? nNear : cntSmall) : cntSmall - nNear;   // bin entries of this pass
   const int nPass = nSmall + (pass == 0 ? cntBig : 0);                           // + the big list in pass 0
-  const int G = min(kBatch, max(1, (nPass + p.batchDiv - 1) / p.batchDiv));   // triangles per batch: a short bin is spread over the warps
-  const int nBatches = (nPass + G - 1) / G;
+  const int G = sPlan[0];          // triangles per batch = min(kBatch, ceil(nPass / batch_div)): a short bin is spread over the warps
+  const int nBatches = sPlan[1];   // ceil(nPass / G)
   for (;;) {
     // batch j takes the entries j, j + nBatches, j + 2 nBatches, ... (interleave = 1, the default):
     // every warp gets a sample of the whole bin instead of one spatially coherent chunk, which evens
@@ -951,12 +962,13 @@ raster_kernel(const RasterParams p) {
       }
     }
   }
-  // Output tile through shared memory + bulk async copies (TMA, cp.async.bulk): the 24 B/px of a tile that lies
+  // Option bulk_out (off: measured slower, raster 0.268 -> 0.289 ms -- every CTA ends waiting for its copies to drain, and
+  // the scalar stores it replaces were never the bound).  Output tile through shared memory + bulk async copies (TMA, cp.async.bulk): the 24 B/px of a tile that lies
   // inside a 16-byte aligned image are staged in the (by now dead) per-warp batch buffers and leave as 3 x TS
   // row copies of 128 / 256 / 384 contiguous bytes instead of five scalar stores per pixel, three of them at a
   // 12-byte stride.  Border tiles, odd widths and strips keep the direct stores.
   constexpr bool kStageFits = NPIX * 24 <= (NTH / 32) * kWarpSmemBytes;
-  const bool bulkOut = kStageFits && (p.exp & 4) && stripLog == 0 && ((p.W & 3) == 0) && tileX0 + TS <= p.W && tileY0 + TS <= p.H &&
+  const bool bulkOut = kStageFits && p.bulkOut && stripLog == 0 && ((p.W & 3) == 0) && tileX0 + TS <= p.W && tileY0 + TS <= p.H &&
                        ((reinterpret_cast<uintptr_t>(p.face) | reinterpret_cast<uintptr_t>(p.bary) | reinterpret_cast<uintptr_t>(p.render)) & 15) == 0;
   int* sFace = reinterpret_cast<int*>(smemRaw + ZRAY);
   float2* sBary = reinterpret_cast<float2*>(smemRaw + ZRAY + NPIX * 4);
@@ -1173,7 +1185,7 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   p.texture = a.texture; p.texcoords = a.texcoords; p.sh_coeff = a.sh_coeff;
   p.bary = a.bary; p.face = a.face; p.render = a.render; p.ctaTrace = a.s.ctaTrace;
   p.C = a.C; p.N = a.N; p.F = a.F; p.W = a.W; p.H = a.H; p.texH = a.texH; p.texW = a.texW;
-  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.batchDiv = a.batchDiv; p.interleave = a.interleave; p.hiz = a.hiz; p.hizMin = a.hizMin; p.spanZ = a.spanZ; p.texBilinear = a.texBilinear; p.resolvePrefetch = a.resolvePrefetch; p.exp = a.exp;
+  p.albedo = a.albedo; p.shading = a.shading; p.tilesX = a.tilesX; p.nT = a.nT; p.cullMargin = a.cullMargin; p.invC = 1.f / (float)a.C; p.batchDiv = a.batchDiv; p.interleave = a.interleave; p.hiz = a.hiz; p.hizMin = a.hizMin; p.spanZ = a.spanZ; p.texBilinear = a.texBilinear; p.resolvePrefetch = a.resolvePrefetch; p.bulkOut = a.bulkOut;
   p.grid2d = nItems <= 65535 ? 1 : 0;
   const dim3 gridT = p.grid2d ? dim3((unsigned)V, (unsigned)nItems) : dim3((unsigned)nItems * (unsigned)V);
   tm->begin(K_RASTER, st);
@@ -1182,7 +1194,6 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
 #define GVV_RASTER_ATTR(TS, RC, NTH) cudaFuncSetAttribute(raster_kernel<TS, RC, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<TS, RC, NTH>())
     GVV_RASTER_ATTR(16, true, 256); GVV_RASTER_ATTR(32, true, 256); GVV_RASTER_ATTR(16, false, 256); GVV_RASTER_ATTR(32, false, 256);
     GVV_RASTER_ATTR(16, false, 128); GVV_RASTER_ATTR(32, false, 128); GVV_RASTER_ATTR(32, false, 1024);
-    cudaFuncSetAttribute(raster_kernel<32, false, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem_bytes<32, false, 256>());
 #undef GVV_RASTER_ATTR
   }
   // The heavy launch goes FIRST, so that its one-SM CTAs are placed while the SMs are empty (behind the small CTAs
@@ -1215,7 +1226,6 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
     } else {
       if (a.rayCache) GVV_RASTER_LAUNCH(32, true, 256);
       else if (a.ctaThreads == 128) GVV_RASTER_LAUNCH(32, false, 128);
-      else if (a.exp & 32) { cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = raster_smem_bytes<32, false, 256>(); cudaLaunchKernelEx(&cfg, raster_kernel<32, false, 256, 3>, p); }
       else GVV_RASTER_LAUNCH(32, false, 256);
     }
 #undef GVV_RASTER_LAUNCH

@@ -87,7 +87,7 @@ struct gvv_renderer {
   int ctaThreads = 256;       // raster: threads per tile CTA (256 | 128)
   int batchDiv = 8;           // raster: a bin of n triangles is cut into batches of ceil(n / batchDiv) (<= 32) triangles
   int bwdPersistent = 0;      // (measured slower: 0.272 vs 0.218 ms) backward: persistent pixel-gradient kernel with a TMA face-tile ring (whole-tile images); 0 = one tile per CTA
-  int exp = 0;                // development: bit mask of experimental code paths under A/B measurement (tools/gpu_ab.py); 0 in production
+  int bulkOut = 0;            // raster: write the tile's outputs through shared memory + TMA bulk copies (measured slower: 0.268 -> 0.289 ms)
   int rayCache = 0;           // raster: 1 = per-pixel ray cache in shared memory (3 CTAs/SM), 0 = recompute (4 CTAs/SM, measured faster)
   float cullMargin = 0.0625f; // px (fixed part of the margin); < 0 disables the conservative screen-space pre-test
   bool hasTexcoords = false;
@@ -108,7 +108,7 @@ namespace gvv {
 
 struct FwdArgs {
   int B, C, N, F, W, H, texH, texW, albedo, shading;
-  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, hizMin, spanZ, splitUnit, heavyThr, heavyMode, heavySlots, ctaSlots, spreadEmpty, texBilinear, resolvePrefetch, chain, exp;
+  int tile, tilesX, tilesY, nT, rayCache, batchDiv, ctaThreads, interleave, hiz, hizMin, spanZ, splitUnit, heavyThr, heavyMode, heavySlots, ctaSlots, spreadEmpty, texBilinear, resolvePrefetch, chain, bulkOut;
   float cullMargin;
   const float *vertex_pos, *vertex_color, *texture, *sh_coeff, *extrinsics, *intrinsics;
   const float* texcoords;
@@ -119,7 +119,7 @@ struct FwdArgs {
 };
 
 struct BwdArgs {
-  int B, C, N, F, W, H, texH, texW, albedo, shading, imgFilter, texBilinear, chain, sharedBatch, exp, bwdPersistent, ctaSlots;
+  int B, C, N, F, W, H, texH, texW, albedo, shading, imgFilter, texBilinear, chain, sharedBatch, bwdPersistent, ctaSlots;
   const float *render_grad, *target_grad, *vertex_pos, *vertex_color, *texture, *sh_coeff, *target_image,
       *vertex_normal, *bary, *extrinsics, *intrinsics, *texcoords, *target_du, *target_dv;
   const int32_t* face;

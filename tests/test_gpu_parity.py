@@ -324,6 +324,29 @@ def test_batched_call_equals_per_element_calls():
     r.close()
 
 
+@pytest.mark.parametrize("albedo,shading,with_target", [("vertexColor", "shaded", False), ("textured", "shaded", True), ("textured", "shadeless", False)])
+def test_persistent_backward_variant_matches_one_tile_per_cta(albedo, shading, with_target):
+    """Option bwd_persistent (persistent CTAs pulling tiles from a counter, face tiles through a TMA ring on mbarriers;
+    off by default, measured slower) computes the same gradients as the one-tile-per-CTA kernel; it only engages on
+    images made of whole 32x32 tiles, so the odd-sized call must fall back silently."""
+    for (W, H) in ((256, 192), (200, 168)):
+        sc = synthetic.make_scene(kind="sphere", rings=48, segments=56, cameras=3, width=W, height=H, batch=2, tex=32, seed=5)
+        ins = [T(sc[k]) for k in INPUT_KEYS]
+        r = make(sc, albedo, shading)
+        out = r.forward(*ins)
+        rg = torch.randn(out[2].shape, generator=torch.Generator().manual_seed(4)).to(dev())
+        tg = torch.randn(out[2].shape, generator=torch.Generator().manual_seed(6)).to(dev()) if with_target else None
+        args = (rg, tg, ins[0], ins[1], ins[2], ins[3], ins[4], out[3], out[0], out[1], ins[5], ins[6])
+        g0 = [t.clone() for t in r.backward(*args)]
+        r.set_option("bwd_persistent", 1)
+        n0 = r.launch_count
+        g1 = r.backward(*args)
+        assert r.launch_count - n0 == (3 if shading == "shaded" else 2)
+        for name, a, b in zip(("vertex_pos_grad", "vertex_color_grad", "texture_grad", "sh_coeff_grad"), g1, g0):
+            assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) <= 2e-5, (name, W, H)     # summation order only
+        r.close()
+
+
 def test_uv_space_normal_map_matches_cpu_oracle():
     """compute_normal_map: rasterisation is replaced by the UV-space normal map."""
     from oracle import cpu
@@ -457,7 +480,7 @@ OPTION_SETS = [
     {"hiz": 0}, {"span_z": 0}, {"span_z": 1}, {"hiz": 0, "span_z": 0, "cull_margin_milli": 250},
     {"split_unit": 48}, {"split_unit": 16, "hiz": 0}, {"heavy_mode": 2, "heavy_thr": 32}, {"heavy_mode": 2, "heavy_thr": 32, "heavy_slots": 3},
     {"heavy_mode": 0}, {"spread_empty": 1}, {"spread_empty": 1, "split_unit": 32}, {"cta_threads": 128}, {"tile": 16}, {"tile": 16, "split_unit": 24},
-    {"interleave": 0}, {"batch_div": 3}, {"batch_div": 24}, {"ray_cache": 1}, {"resolve_prefetch": 1},
+    {"interleave": 0}, {"batch_div": 3}, {"batch_div": 24}, {"ray_cache": 1}, {"resolve_prefetch": 1}, {"bulk_out": 1},
 ]
 
 
