@@ -394,10 +394,15 @@ __device__ __forceinline__ void stage_view_constants(const PixelParams& p, int v
   }
 }
 
-// One 32x32 tile per CTA (any image size).  80 registers, 3 CTAs/SM: at 64 registers (4 CTAs/SM) the per-pixel chain
-// spilled ~90 bytes in its hot path -- local-memory traffic through the same L1 data pipe that bounds the kernel.
+// One 32x32 tile per CTA (any image size).  The shaded instances run at 80 registers, 3 CTAs/SM: at 64 registers
+// (4 CTAs/SM) the per-pixel chain spilled ~90 bytes in its hot path -- local-memory traffic through the same L1 data
+// pipe that bounds the kernel (vertexColor + shaded: 0.236 -> 0.214 ms).  The shadeless instances fit 64 registers
+// without spilling and keep 4 CTAs/SM (textured + shadeless, 32 views: 0.29 ms against 0.33 ms at 3 CTAs/SM).
 template <bool SHADED, int ALBEDO>
-__global__ void __launch_bounds__(256, 3)
+constexpr int pixel_grad_ctas_per_sm() { return SHADED ? 3 : 4; }      // (textured + shaded, 32 views: 0.617 ms at 3, 0.635 ms at 4)
+
+template <bool SHADED, int ALBEDO>
+__global__ void __launch_bounds__(256, (pixel_grad_ctas_per_sm<SHADED, ALBEDO>()))
 pixel_grad_kernel(const PixelParams p) {
   chain_wait(); chain_trigger();
   extern __shared__ __align__(16) float buf_dyn[];   // per warp: (kVals + kShRows + kIdRows) rows, value-major, kRow floats per value (32 pixels + pad)
