@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """compute-sanitizer target: small forward+backward calls through every kernel path (all albedo modes,
-16/32 tiles, big-triangle list, strip split, heavy-tile launch, bilinear texture, normal map, helpers).
+16/32 tiles, big-triangle list, strip split, heavy-tile launch, bilinear texture, the TMA options (persistent backward with
+its face-tile ring, bulk output tile), normal map, helpers).
   compute-sanitizer --tool memcheck  python tools/gpu_sanitize_target.py
   compute-sanitizer --tool racecheck python tools/gpu_sanitize_target.py"""
 import os, sys
@@ -20,7 +21,7 @@ for kind, kw in (("sphere", dict(rings=16, segments=20, cameras=2, width=100, he
     ins = [T(sc[k]) for k in KEYS]
     B = ins[0].shape[0]
     for albedo, shading in (("vertexColor", "shaded"), ("textured", "shaded"), ("textured", "shadeless"), ("normal", "shaded"), ("foregroundMask", "shaded")):
-        for opts in ({}, {"tile": 16}, {"split_unit": 8, "heavy_thr": 16, "heavy_mode": 2}, {"texture_bilinear": 1, "cull_margin_milli": -1}, {"span_z": 1, "hiz": 0}):
+        for opts in ({}, {"tile": 16}, {"split_unit": 8, "heavy_thr": 16, "heavy_mode": 2}, {"texture_bilinear": 1, "cull_margin_milli": -1}, {"span_z": 1, "hiz": 0}, {"bwd_persistent": 1, "bulk_out": 1}):
             r = _native.NativeRenderer(sc["faces"], sc["texcoords"], N, C, W, H, albedo, shading, 1, 1, False, dev)
             for k, v in opts.items():
                 r.set_option(k, v)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Turns the scratch artefacts of a gpurun session (gpurun_out/) into the tracked summaries under profiles/:
   python tools/summarize_profiles.py <tag> <launches.csv> <prof.ncu-rep>
-writes profiles/<tag>_launches_bench_summary.md, appends a section to profiles/r01_ncu_summaries.md and
+writes profiles/<tag>_launches_bench_summary.md, appends a section to profiles/<round of the tag>_ncu_summaries.md and
 refreshes profiles/traffic.json (dram read+write bytes per launch of the two big kernels)."""
 import csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -41,9 +41,20 @@ want = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__occup
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_active.avg", "sm__cycles_elapsed.max",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed_op_shared_atom.sum", "smsp__inst_executed_op_global_red.sum",
-        "lts__t_sectors_op_red.sum", "lts__t_sectors_op_atom.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_local_op_st.sum", "l1tex__t_sector_hit_rate.pct",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum", "lts__t_sectors_srcunit_tex_op_red.sum", "lts__t_sectors_srcunit_tex_op_red.sum.pct_of_peak_sustained_elapsed",
+        "lts__t_sectors_srcunit_tex_op_red.sum.per_second", "lts__t_sectors_srcunit_tex_op_atom.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
 traffic = {}
-with open(os.path.join(ROOT, "profiles", "r01_ncu_summaries.md"), "a") as f:
+summary_md = os.path.join(ROOT, "profiles", f"{tag[:3]}_ncu_summaries.md")
+if not os.path.exists(summary_md):
+    open(summary_md, "w").write(f"# ncu --set full summaries, round {int(tag[1:3])} (B200, config 2: 8 views, 1024x1024, 70k tris)\n"
+                                "# `ncu --set full --clock-control none --import-source on -k regex:\"raster_kernel|pixel_grad\" --launch-skip 2 --launch-count 2 python tools/gpu_profile_target.py`\n"
+                                "# (per-kernel counters; L2 atomics = lts__t_sectors_srcunit_tex_op_red, percentage of the L2's own peak)\n")
+with open(summary_md, "a") as f:
     f.write(f"\n## {tag}: {title}\n")
     for r in rr[2:]:
         d = dict(zip(h, r))
