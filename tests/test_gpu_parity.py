@@ -508,6 +508,29 @@ def test_every_tuning_knob_keeps_the_bits(opts):
     base.close(); r.close()
 
 
+def test_heavy_tile_pair_stress_changing_geometry():
+    """The heavy-tile launch and the 256-thread launch that follows it as a programmatic dependent launch overlap on
+    purpose; the small CTAs read what the binning kernels wrote BEFORE the pair without a griddepcontrol.wait of their
+    own.  Stress: 60 calls with geometry that changes every call (so a stale bin, offset or camera record
+    would show), each compared bit for bit with a handle that never uses the pair."""
+    sc = synthetic.make_scene(kind="sphere", rings=90, segments=96, cameras=2, width=320, height=256, tex=16, seed=12)
+    pair, plain = make(sc, "vertexColor", "shaded"), make(sc, "vertexColor", "shaded")
+    for k, v in {"heavy_mode": 2, "heavy_thr": 24, "heavy_slots": 16}.items():
+        pair.set_option(k, v)
+    plain.set_option("heavy_mode", 0)
+    ins = [T(sc[k]) for k in INPUT_KEYS]
+    gen = torch.Generator(device="cpu").manual_seed(21)
+    base_pos = ins[0].clone()
+    n0 = pair.launch_count
+    for it in range(60):
+        ins[0] = base_pos * (1.0 + 0.15 * float(torch.rand((), generator=gen))) + (torch.rand(base_pos.shape, generator=gen) * 4.0).to(dev())
+        a, b = pair.forward(*ins), plain.forward(*ins)
+        for x, y in zip(a[:4], b[:4]):
+            assert torch.equal(x.view(torch.int32) if x.dtype == torch.float32 else x, y.view(torch.int32) if y.dtype == torch.float32 else y), it
+    assert pair.launch_count - n0 == 60 * 7          # the pair really ran: seven launches per forward instead of six
+    pair.close(); plain.close()
+
+
 @pytest.mark.skipif(torch.cuda.is_available() and torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
 def test_two_devices_in_one_process():
     """Handles on two devices of the same process (the shared-memory opt-ins are per device): same bits on both."""
