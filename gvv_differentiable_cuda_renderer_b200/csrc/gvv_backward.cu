@@ -52,9 +52,9 @@ struct PixelParams {
 
 constexpr int kVals = 27;
 constexpr int kShRows = 12;  // rows 27..38 of the warp buffer: g*albedo (3) and the SH basis (9) of every pixel, for the SH gradient
-constexpr int kWarpBufFloats = (27 + 12 + 3) * 36;
 constexpr int kIdRows = 3;   // rows 39..41: the three vertex ids of every pixel's triangle (int bits), read at the end of a run
 constexpr int kRow = 36;    // 32 pixels + 4 pad: a quarter-warp's float4 reads of 8 different rows hit 32 different banks
+constexpr int kWarpBufFloats = (kVals + kShRows + kIdRows) * kRow;
 
 // Tolerance-level arithmetic of the backward: reciprocal-multiply instead of IEEE divides
 // (gradients are compared to rel-L2 1e-4; the visibility-critical ray uses the exact functions).

@@ -734,7 +734,6 @@ raster_kernel(const RasterParams p) {
     }
   };
 
-  const int cntAll = cntSmall + cntBig;
   const int* smallList = p.bins + (size_t)view * p.F * kMaxSmallTiles + p.tileOffset[tidx];
   const int* bigList = p.bigList + (size_t)view * p.F;
   const float4* vs = p.vscaled + (size_t)b * p.N;
