@@ -6,11 +6,13 @@
 //
 //   prep_kernel          camera records (ref :17-61), zero fill of all four gradient outputs + the vertex-normal
 //                        gradient (ref :68-107), repack of the caller's 12-byte vertex arrays to float4
-//   pixel_grad_kernel    one warp per 32-pixel scanline segment.  The 27 per-vertex values of a
+//   pixel_grad_kernel    one warp per 32-pixel scanline segment (segment_grad).  The 27 per-vertex values of a
 //                        pixel (9 colour, 9 position, 9 vertex-normal gradient) are transposed
 //                        through shared memory so that lane j sums value j over each run of
 //                        pixels that see the same triangle: ONE warp-wide atomic per run instead
 //                        of 27 per pixel.  SH gradients are reduced warp -> block -> 27 atomics.
+//                        (pixel_grad_persistent_kernel: the same segments driven by persistent CTAs with a
+//                        TMA ring of face tiles -- option bwd_persistent, measured slower, off.)
 //   normal_term_kernel   mesh-space pass for the vertex-normal -> position term (ref :559-615):
 //                        the reference loops over every face incident to the pixel's three
 //                        vertices (27*deg atomics per pixel); that sum is linear in the per-pixel
