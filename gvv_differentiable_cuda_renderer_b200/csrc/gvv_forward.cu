@@ -19,6 +19,7 @@
 //
 // No global z-buffer exists: the z-tile lives in shared memory, so HBM sees only the compulsory
 // output stores (24 B/px) plus the (L2-resident) mesh reads.  camera_kernel is only used by the normal-map path.
+#include <algorithm>
 #include "gvv_internal.h"
 
 namespace gvv {
@@ -185,50 +186,96 @@ constexpr int kBinFacesPerThread = 4;
 // the FAR ones from the back (bin_fill_kernel), so that the raster warps set every triangle up exactly once.
 constexpr int kNoBound = (int)0x80000000;   // key_lower_bound of a triangle without a usable bound: always "near"
 
-template <bool SMEM_HIST>
+// Shared-memory histograms cover a WINDOW of the tile grid: the band of tile rows [ty0, ty1] that the block's
+// kBinFacesPerThread * 256 consecutive triangles touch (the whole grid when it has at most kBinWindow tiles).  Meshes
+// are stored spatially coherent, so the band is short; clearing and flushing it costs O(band) instead of O(nT) per
+// block -- at 3840x2160 (8160 tiles) the three full-grid sweeps were 70 % of the kernel and the 98 / 130 KB of shared
+// memory they needed left one block per SM.  A block whose band does not fit falls back to global atomics.
+constexpr int kBinWindow = 2560;   // tiles per window: 30 KB (count) / 40 KB (fill) of shared memory per block
+
+struct BinWindow { int t0, n; bool local; };   // first tile of the band, tiles in it, fits in shared memory
+
+// r[k].n > 0 marks the triangles that go to the bins; ty0 / ty1 of those define the band (block-wide min / max)
+template <bool WINDOWED>
+__device__ __forceinline__ BinWindow bin_window(const TileRange* r, int tilesX, int tilesY, int nT, int* wb) {
+  BinWindow w;
+  if (!WINDOWED) { w.t0 = 0; w.n = nT; w.local = true; return w; }      // nT <= kBinWindow: the window is the whole grid
+  if (threadIdx.x == 0) { wb[0] = 0x7fffffff; wb[1] = -1; }
+  __syncthreads();
+  int lo = 0x7fffffff, hi = -1;
+#pragma unroll
+  for (int k = 0; k < kBinFacesPerThread; ++k)
+    if (r[k].n > 0 && r[k].n <= kMaxSmallTiles) { lo = min(lo, r[k].ty0); hi = max(hi, r[k].ty1); }
+  lo = __reduce_min_sync(FULL_MASK, lo); hi = __reduce_max_sync(FULL_MASK, hi);
+  if ((threadIdx.x & 31) == 0 && hi >= 0) { atomicMin(&wb[0], lo); atomicMax(&wb[1], hi); }
+  __syncthreads();
+  lo = wb[0]; hi = wb[1];
+  (void)tilesY;
+  w.t0 = hi >= 0 ? lo * tilesX : 0;
+  w.n = hi >= 0 ? (hi - lo + 1) * tilesX : 0;
+  w.local = w.n <= kBinWindow;
+  return w;
+}
+
+template <bool WINDOWED>
 __global__ void __launch_bounds__(256)
 bin_count_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj, int* __restrict__ tileCount,
                  int* __restrict__ tileMinK, int* __restrict__ tileMaxK,
                  int* __restrict__ bigCount, int* __restrict__ bigList, int F, int N, int W, int H, int tileShift,
-                 int tilesX, int nT) {
+                 int tilesX, int tilesY, int nT) {
   chain_wait(); chain_trigger();
-  extern __shared__ int hist[];   // SMEM_HIST: hist[nT], mn[nT], mx[nT]
-  int* mn = hist + nT;
-  int* mx = hist + 2 * nT;
+  extern __shared__ int hist[];   // hist[cap], mn[cap], mx[cap], cap = min(nT, kBinWindow)
+  __shared__ int wb[2];
+  const int cap = min(nT, kBinWindow);
+  int* mn = hist + cap;
+  int* mx = hist + 2 * cap;
   const int view = blockIdx.y;
-  if (SMEM_HIST) {
-    for (int i = threadIdx.x; i < nT; i += blockDim.x) { hist[i] = 0; mn[i] = 0x7fffffff; mx[i] = kNoBound; }
+  TileRange r[kBinFacesPerThread];
+  if (WINDOWED) {      // the band must be known before the first add: all tile ranges first
+#pragma unroll
+    for (int k = 0; k < kBinFacesPerThread; ++k) {
+      const int f = (blockIdx.x * kBinFacesPerThread + k) * blockDim.x + threadIdx.x;
+      r[k].n = 0; r[k].tx0 = r[k].ty0 = 0; r[k].tx1 = r[k].ty1 = -1; r[k].klb = kNoBound;
+      if (f < F) r[k] = tile_range(faces4, proj + (size_t)view * N, f, W, H, tileShift);
+    }
+  }
+  const BinWindow w = bin_window<WINDOWED>(r, tilesX, tilesY, nT, wb);
+  int* gCount = tileCount + (size_t)view * nT;
+  int* gMin = tileMinK + (size_t)view * nT;
+  int* gMax = tileMaxK + (size_t)view * nT;
+  if (w.local) {
+    for (int i = threadIdx.x; i < w.n; i += blockDim.x) { hist[i] = 0; mn[i] = 0x7fffffff; mx[i] = kNoBound; }
     __syncthreads();
   }
 #pragma unroll
   for (int k = 0; k < kBinFacesPerThread; ++k) {
     const int f = (blockIdx.x * kBinFacesPerThread + k) * blockDim.x + threadIdx.x;
     if (f >= F) continue;
-    const TileRange r = tile_range(faces4, proj + (size_t)view * N, f, W, H, tileShift);
-    if (r.n > kMaxSmallTiles) {
+    const TileRange q = WINDOWED ? r[k] : tile_range(faces4, proj + (size_t)view * N, f, W, H, tileShift);
+    if (q.n > kMaxSmallTiles) {
       const int slot = atomicAdd(bigCount + view, 1);
       bigList[(size_t)view * F + slot] = f;
-    } else if (r.n > 0) {
-      for (int ty = r.ty0; ty <= r.ty1; ++ty)
-        for (int tx = r.tx0; tx <= r.tx1; ++tx) {
+    } else if (q.n > 0) {
+      for (int ty = q.ty0; ty <= q.ty1; ++ty)
+        for (int tx = q.tx0; tx <= q.tx1; ++tx) {
           const int t = ty * tilesX + tx;
-          if (SMEM_HIST) {
-            atomicAdd(&hist[t], 1);
-            if (r.klb != kNoBound) { atomicMin(&mn[t], r.klb); atomicMax(&mx[t], r.klb); }
+          if (w.local) {
+            atomicAdd(&hist[t - w.t0], 1);
+            if (q.klb != kNoBound) { atomicMin(&mn[t - w.t0], q.klb); atomicMax(&mx[t - w.t0], q.klb); }
           } else {
-            atomicAdd(tileCount + (size_t)view * nT + t, 1);
-            if (r.klb != kNoBound) { atomicMin(tileMinK + (size_t)view * nT + t, r.klb); atomicMax(tileMaxK + (size_t)view * nT + t, r.klb); }
+            atomicAdd(gCount + t, 1);
+            if (q.klb != kNoBound) { atomicMin(gMin + t, q.klb); atomicMax(gMax + t, q.klb); }
           }
         }
     }
   }
-  if (SMEM_HIST) {
+  if (w.local) {
     __syncthreads();
-    for (int i = threadIdx.x; i < nT; i += blockDim.x) {
+    for (int i = threadIdx.x; i < w.n; i += blockDim.x) {
       const int c = hist[i];
       if (c) {
-        atomicAdd(tileCount + (size_t)view * nT + i, c);
-        if (mx[i] != kNoBound) { atomicMin(tileMinK + (size_t)view * nT + i, mn[i]); atomicMax(tileMaxK + (size_t)view * nT + i, mx[i]); }
+        atomicAdd(gCount + w.t0 + i, c);
+        if (mx[i] != kNoBound) { atomicMin(gMin + w.t0 + i, mn[i]); atomicMax(gMax + w.t0 + i, mx[i]); }
       }
     }
   }
@@ -358,18 +405,20 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const int* __restrict__ 
   for (int i = extraItems + threadIdx.x; i < nItems; i += blockDim.x) order[i] = -1;
 }
 
-template <bool SMEM_HIST>
+template <bool WINDOWED>
 __global__ void __launch_bounds__(256)
 bin_fill_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj, const int* __restrict__ tileOffset,
                 const int* __restrict__ tileCount, const int* __restrict__ tileThr,
                 int* __restrict__ tileCursor, int* __restrict__ tileCursorFar, int* __restrict__ bins, int F, int N, int W, int H, int tileShift,
-                int tilesX, int nT) {
+                int tilesX, int tilesY, int nT) {
   chain_wait(); chain_trigger();
-  extern __shared__ int sm[];   // SMEM_HIST: histN[nT], histF[nT], baseN[nT], baseF[nT]
+  extern __shared__ int sm[];   // histN[cap], histF[cap], baseN[cap], baseF[cap] over the block's window (see bin_window), cap = min(nT, kBinWindow)
+  __shared__ int wb[2];
+  const int cap = min(nT, kBinWindow);
   int* histN = sm;
-  int* histF = sm + nT;
-  int* baseN = sm + 2 * nT;
-  int* baseF = sm + 3 * nT;
+  int* histF = sm + cap;
+  int* baseN = sm + 2 * cap;
+  int* baseF = sm + 3 * cap;
   const int view = blockIdx.y;
   TileRange r[kBinFacesPerThread];
   int fid[kBinFacesPerThread];
@@ -380,6 +429,7 @@ bin_fill_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj
     if (fid[k] < F) r[k] = tile_range(faces4, proj + (size_t)view * N, fid[k], W, H, tileShift);
     if (r[k].n > kMaxSmallTiles) r[k].n = 0;      // big triangles live in the big list (bin_count_kernel)
   }
+  const BinWindow w = bin_window<WINDOWED>(r, tilesX, tilesY, nT, wb);
   int* viewBins = bins + (size_t)view * F * kMaxSmallTiles;
   const int* off = tileOffset + (size_t)view * nT;
   const int* cnt = tileCount + (size_t)view * nT;
@@ -388,8 +438,8 @@ bin_fill_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj
   int* curF = tileCursorFar + (size_t)view * nT;
   // a triangle is FAR in a tile when its depth-key lower bound is beyond the tile's threshold
   auto is_far = [&](int klb, int t) { return klb != kNoBound && klb > __ldg(thr + t); };
-  if (SMEM_HIST) {
-    for (int i = threadIdx.x; i < 2 * nT; i += blockDim.x) sm[i] = 0;
+  if (w.local) {
+    for (int i = threadIdx.x; i < w.n; i += blockDim.x) { histN[i] = 0; histF[i] = 0; }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kBinFacesPerThread; ++k)
@@ -397,15 +447,15 @@ bin_fill_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj
         for (int ty = r[k].ty0; ty <= r[k].ty1; ++ty)
           for (int tx = r[k].tx0; tx <= r[k].tx1; ++tx) {
             const int t = ty * tilesX + tx;
-            atomicAdd(is_far(r[k].klb, t) ? &histF[t] : &histN[t], 1);
+            atomicAdd(is_far(r[k].klb, t) ? &histF[t - w.t0] : &histN[t - w.t0], 1);
           }
     __syncthreads();
     // one global reservation per tile and side this block touches: near entries grow from the front of the
     // tile's segment, far entries from its back
-    for (int i = threadIdx.x; i < nT; i += blockDim.x) {
-      const int cN = histN[i], cF = histF[i];
-      if (cN) { baseN[i] = off[i] + atomicAdd(curN + i, cN); histN[i] = 0; }
-      if (cF) { baseF[i] = off[i] + cnt[i] - atomicAdd(curF + i, cF) - cF; histF[i] = 0; }
+    for (int i = threadIdx.x; i < w.n; i += blockDim.x) {
+      const int cN = histN[i], cF = histF[i], t = w.t0 + i;
+      if (cN) { baseN[i] = off[t] + atomicAdd(curN + t, cN); histN[i] = 0; }
+      if (cF) { baseF[i] = off[t] + cnt[t] - atomicAdd(curF + t, cF) - cF; histF[i] = 0; }
     }
     __syncthreads();
 #pragma unroll
@@ -413,9 +463,9 @@ bin_fill_kernel(const int4* __restrict__ faces4, const float4* __restrict__ proj
       if (r[k].n > 0)
         for (int ty = r[k].ty0; ty <= r[k].ty1; ++ty)
           for (int tx = r[k].tx0; tx <= r[k].tx1; ++tx) {
-            const int t = ty * tilesX + tx;
-            if (is_far(r[k].klb, t)) viewBins[baseF[t] + atomicAdd(&histF[t], 1)] = fid[k];
-            else viewBins[baseN[t] + atomicAdd(&histN[t], 1)] = fid[k];
+            const int t = ty * tilesX + tx, i = t - w.t0;
+            if (is_far(r[k].klb, t)) viewBins[baseF[i] + atomicAdd(&histF[i], 1)] = fid[k];
+            else viewBins[baseN[i] + atomicAdd(&histN[i], 1)] = fid[k];
           }
   } else {
 #pragma unroll
@@ -1130,15 +1180,12 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   const int tileShift = a.tile == 32 ? 5 : 4;
   const dim3 gridF((a.F + 256 * kBinFacesPerThread - 1) / (256 * kBinFacesPerThread), V);
   tm->begin(K_BIN_COUNT, st);
-  if (a.nT <= kSmemHistTiles) {
-    static unsigned long long countAttr = 0;
-    if (first_use_on_device(&countAttr)) cudaFuncSetAttribute(bin_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kSmemHistTiles * (int)sizeof(int));
-    launch_chained(a.chain, bin_count_kernel<true>, gridF, dim3(256), 3 * a.nT * sizeof(int), st, a.faces4, a.s.proj, a.s.tileCount, a.s.tileMinK, a.s.tileMaxK,
-                   a.s.bigCount, a.s.bigList, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
-  } else {
-    launch_chained(a.chain, bin_count_kernel<false>, gridF, dim3(256), 0, st, a.faces4, a.s.proj, a.s.tileCount, a.s.tileMinK, a.s.tileMaxK,
-                   a.s.bigCount, a.s.bigList, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
-  }
+  if (a.nT <= kBinWindow)
+    launch_chained(a.chain, bin_count_kernel<false>, gridF, dim3(256), 3 * a.nT * sizeof(int), st, a.faces4, a.s.proj, a.s.tileCount, a.s.tileMinK, a.s.tileMaxK,
+                   a.s.bigCount, a.s.bigList, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.tilesY, a.nT);
+  else
+    launch_chained(a.chain, bin_count_kernel<true>, gridF, dim3(256), 3 * kBinWindow * sizeof(int), st, a.faces4, a.s.proj, a.s.tileCount, a.s.tileMinK, a.s.tileMaxK,
+                   a.s.bigCount, a.s.bigList, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.tilesY, a.nT);
   tm->end(st);
   ++launches;
   tm->begin(K_BIN_SCAN, st);
@@ -1166,15 +1213,12 @@ int launch_forward(const FwdArgs& a, cudaStream_t st, KernelTimer* tm) {
   tm->end(st);
   ++launches;
   tm->begin(K_BIN_FILL, st);
-  if (a.nT <= kSmemHistTiles) {
-    static unsigned long long fillAttr = 0;
-    if (first_use_on_device(&fillAttr)) cudaFuncSetAttribute(bin_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSmemHistTiles * (int)sizeof(int));
-    launch_chained(a.chain, bin_fill_kernel<true>, gridF, dim3(256), 4 * a.nT * sizeof(int), st, a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCount, a.s.tileThr,
-                   a.s.tileCursor, a.s.tileCursorFar, a.s.bins, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
-  } else {
-    launch_chained(a.chain, bin_fill_kernel<false>, gridF, dim3(256), 0, st, a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCount, a.s.tileThr,
-                   a.s.tileCursor, a.s.tileCursorFar, a.s.bins, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.nT);
-  }
+  if (a.nT <= kBinWindow)
+    launch_chained(a.chain, bin_fill_kernel<false>, gridF, dim3(256), 4 * a.nT * sizeof(int), st, a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCount, a.s.tileThr,
+                   a.s.tileCursor, a.s.tileCursorFar, a.s.bins, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.tilesY, a.nT);
+  else
+    launch_chained(a.chain, bin_fill_kernel<true>, gridF, dim3(256), 4 * kBinWindow * sizeof(int), st, a.faces4, a.s.proj, a.s.tileOffset, a.s.tileCount, a.s.tileThr,
+                   a.s.tileCursor, a.s.tileCursorFar, a.s.bins, a.F, a.N, a.W, a.H, tileShift, a.tilesX, a.tilesY, a.nT);
   tm->end(st);
   ++launches;
   RasterParams p;

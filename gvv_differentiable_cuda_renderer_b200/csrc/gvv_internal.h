@@ -13,7 +13,6 @@ namespace gvv {
 // the bin pool by F*kMaxSmallTiles entries per view without ever reading a count back to the host.
 constexpr int kMaxSmallTiles = 16;
 constexpr int kMaxTiles = 40960;       // bin_scan_kernel keeps a view's tile histogram in shared memory (160 KB): e.g. 6400 x 6400 pixels at 32 x 32
-constexpr int kSmemHistTiles = 12288;  // largest tile grid handled with shared-memory histograms (3840x2160 at 32x32 = 8160 tiles; bin_fill needs 16 B per tile: 192 KB)
 
 struct Scratch {
   int capViews = 0, capBatch = 0;

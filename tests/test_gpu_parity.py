@@ -171,13 +171,19 @@ def test_cuda_matches_reference_cuda_core_live(albedo, shading, size, rings, seg
 
 
 @pytest.mark.skipif(not _ref_available(), reason="oracle/_ref/libgvv_ref.so not shipped")
-@pytest.mark.parametrize("albedo", ["normal", "textured", "lighting"])
-def test_stress_resolution_4k_matches_reference(albedo):
+@pytest.mark.parametrize("albedo,shuffled", [("normal", False), ("textured", False), ("lighting", False), ("normal", True)])
+def test_stress_resolution_4k_matches_reference(albedo, shuffled):
     """BASELINE.json config 5 shape (3840x2160, forward, visibility bound) at a triangle count the
-    reference's O(N*F) constructor can still digest; 8160 tiles exercises the global-atomic binning path."""
+    reference's O(N*F) constructor can still digest.  8160 tiles: the binning kernels keep their histograms over a
+    window of tile rows per block (ring-ordered faces: short bands); with the face order shuffled every block's band
+    is the whole image, which does not fit the window and takes the global-atomic fallback."""
     from oracle import ref as oref
     sc = synthetic.make_scene(kind="sphere", rings=160, segments=200, cameras=1, width=3840, height=2160, tex=256, seed=3,
                               coverage_radius_frac=0.26)
+    if shuffled:
+        perm = np.random.default_rng(5).permutation(len(sc["faces"]))
+        sc["faces"] = np.ascontiguousarray(sc["faces"][perm])
+        sc["texcoords"] = np.ascontiguousarray(sc["texcoords"][perm])      # [F, 3, 2], per-corner
     N, W, H = sc["num_vertices"], 3840, 2160
     ins = [T(sc[k]) for k in INPUT_KEYS]
     ref = oref.RefRenderer(sc["faces"], sc["texcoords"], N, 1, W, H, albedo, "shaded", with_backward=False)
