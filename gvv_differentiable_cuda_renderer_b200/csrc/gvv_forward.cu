@@ -693,16 +693,16 @@ raster_kernel(const RasterParams p) {
       const size_t rowBase = pixBase + (size_t)tileY0 * p.W + tileX0;
       for (int i = tid; i < rowsValid * (TS / 4); i += NTH) {
         const int r = i / (TS / 4), c = i % (TS / 4);
-        reinterpret_cast<int4*>(p.face + rowBase + (size_t)r * p.W)[c] = make_int4(-1, -1, -1, -1);
+        __stcs(reinterpret_cast<int4*>(p.face + rowBase + (size_t)r * p.W) + c, make_int4(-1, -1, -1, -1));
       }
       for (int i = tid; i < rowsValid * (TS / 2); i += NTH) {
         const int r = i / (TS / 2), c = i % (TS / 2);
-        reinterpret_cast<float4*>(p.bary + 2 * (rowBase + (size_t)r * p.W))[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __stcs(reinterpret_cast<float4*>(p.bary + 2 * (rowBase + (size_t)r * p.W)) + c, make_float4(0.f, 0.f, 0.f, 0.f));
       }
       for (int i = tid; i < rowsValid * (3 * TS / 4); i += NTH) {
         const int r = i / (3 * TS / 4), c = i % (3 * TS / 4), m = c % 3;   // (0,1,0,0) (1,0,0,1) (0,0,1,0)
-        reinterpret_cast<float4*>(p.render + 3 * (rowBase + (size_t)r * p.W))[c] =
-            make_float4(m == 1 ? 1.f : 0.f, m == 0 ? 1.f : 0.f, m == 2 ? 1.f : 0.f, m == 1 ? 1.f : 0.f);
+        __stcs(reinterpret_cast<float4*>(p.render + 3 * (rowBase + (size_t)r * p.W)) + c,
+               make_float4(m == 1 ? 1.f : 0.f, m == 0 ? 1.f : 0.f, m == 2 ? 1.f : 0.f, m == 1 ? 1.f : 0.f));
       }
       return;
     }
@@ -710,9 +710,9 @@ raster_kernel(const RasterParams p) {
       const int x = tileX0 + (q % TS), y = tileY0 + (q / TS);
       if (x < p.W && y < p.H) {
         const size_t pix = pixBase + (size_t)y * p.W + x;
-        p.face[pix] = -1;
-        reinterpret_cast<float2*>(p.bary)[pix] = make_float2(0.f, 0.f);
-        p.render[3 * pix + 0] = 0.f; p.render[3 * pix + 1] = 1.f; p.render[3 * pix + 2] = 0.f;
+        __stcs(p.face + pix, -1);
+        __stcs(reinterpret_cast<float2*>(p.bary) + pix, make_float2(0.f, 0.f));
+        __stcs(p.render + 3 * pix + 0, 0.f); __stcs(p.render + 3 * pix + 1, 1.f); __stcs(p.render + 3 * pix + 2, 0.f);
       }
     }
     return;
@@ -1094,9 +1094,11 @@ raster_kernel(const RasterParams p) {
       sBary[q] = make_float2(a, bq);
       sRender[3 * q + 0] = cr; sRender[3 * q + 1] = cg; sRender[3 * q + 2] = cb;
     } else {
-      p.face[pix] = faceId;
-      reinterpret_cast<float2*>(p.bary)[pix] = make_float2(a, bq);
-      p.render[3 * pix + 0] = cr; p.render[3 * pix + 1] = cg; p.render[3 * pix + 2] = cb;
+      // streaming (evict-first) stores: 24 B/px of outputs that nothing re-reads soon must not displace the mesh
+      // arrays and bins from L2 / the stores' own lines from each other (raster 0.268 -> 0.263 ms with the background path)
+      __stcs(p.face + pix, faceId);
+      __stcs(reinterpret_cast<float2*>(p.bary) + pix, make_float2(a, bq));
+      __stcs(p.render + 3 * pix + 0, cr); __stcs(p.render + 3 * pix + 1, cg); __stcs(p.render + 3 * pix + 2, cb);
     }
   }
   if (bulkOut) {
